@@ -1,0 +1,102 @@
+// kernels.cuh -- launch wrappers of the sm_100a kernels (definitions in kernels_*.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include "mgb_internal.h"
+
+namespace mgb {
+
+extern long long g_launches;   // number of kernel launches issued by this library
+
+// ---- halo (single-GPU part: physical edges; src/mg_mpi_exchange.f90) ---------------------------------
+// nh = 1 array a(nzl, 0:ny+1, 0:nx+1): homogeneous-Neumann mirror on edges without neighbour, physical corners.
+void launch_halo1_phys(cudaStream_t st, double* a, int nzl, int ny, int nx, Halo1Flags f);
+// corners that depend on just-received halos ("flag_*" logic, src/mg_mpi_exchange.f90:720-743)
+void launch_halo1_flagcorners(cudaStream_t st, double* a, int nzl, int ny, int nx, Halo1Flags f);
+// nh = 2 array a(nzl, -1:ny+2, -1:nx+2) (zr, zw): ring 1 mirror, ring 2 = 2A-B, corners point mirror
+void launch_halo2_phys(cudaStream_t st, double* a, int nzl, int ny, int nx, Halo1Flags f);
+void launch_halo2_flagcorners(cudaStream_t st, double* a, int nzl, int ny, int nx, Halo1Flags f);
+// pack / unpack of strided S/N faces and nh-wide E/W faces for the inter-GPU exchange
+void launch_pack_rows(cudaStream_t st, const double* a, double* buf, int nzl, int ny, int nx, int nh, int j0, int nrows, int i0, int ncols);
+void launch_unpack_rows(cudaStream_t st, double* a, const double* buf, int nzl, int ny, int nx, int nh, int j0, int nrows, int i0, int ncols);
+
+// ---- relaxation (src/mg_relax.f90:151-334) -------------------------------------------------------------
+struct ColourSet {     // columns visited by one colour of a sweep
+  int istart, istep;   // i = istart, istart+istep, ... <= nx
+  int jrule;           // 0: j = 1 + mod(i+rb,2), step 2 (red-black);  1: j = jfix, step 2 (four-colour)
+  int rb, jfix;
+  int bottom_mode;     // 0: no k=1 diagonal terms ('simple');  1: rank-1 form (two (i+1) terms from the x1 snapshot);
+                       // 2: all four terms read from p (no same-colour coupling, four-colour)
+};
+void launch_snapshot_x1(cudaStream_t st, const LevelView& L);
+void launch_relax_A(cudaStream_t st, const LevelView& L, const ColourSet& cs);
+void launch_relax_B(cudaStream_t st, const LevelView& L, const ColourSet& cs);
+void launch_relax_C(cudaStream_t st, const LevelView& L, const ColourSet& cs);
+
+// ---- residual + norm (src/mg_relax.f90:337-515) ----------------------------------------------------------
+// r = b - A p on the interior; partial sums of r^2 per block into `partials`, then reduced in fixed order to *sum_out.
+int  residual_num_partials(const LevelView& L);
+void launch_residual(cudaStream_t st, const LevelView& L, int real_matrix, double* partials, double* sum_out);
+void launch_sumsq(cudaStream_t st, const LevelView& L, const double* a, double* partials, double* sum_out);
+
+// ---- intergrid (src/mg_intergrids.f90) -------------------------------------------------------------------
+// y_c(k2,j2,i2) = sum of the 8 fine cells of x_f ; y has local dims (nxc,nyc,nzc) with 1 halo
+void launch_restrict8(cudaStream_t st, const double* xf, int nzf, int nyf, int nxf, double* yc, int nzc, int nyc, int nxc);
+// trilinear/nearest prolongation of xc (nzc,nyc,nxc) onto the fine interior.
+// mode 0: rf = interp           (reference's first step; halo(rf) and p+=rf done by the caller)
+// mode 1: pf += interp          (fused; caller refreshes halo(pf))
+void launch_prolong(cudaStream_t st, const double* xc, int nzc, int nyc, int nxc, double* rf, double* pf, int linear, int mode);
+void launch_axpy_all(cudaStream_t st, double* y, const double* x, size_t n);          // y += x
+void launch_add_halo_ring(cudaStream_t st, double* p, const double* r, int nz, int ny, int nx);  // p += r on the halo ring only
+void launch_fill(cudaStream_t st, double* a, double v, size_t n);
+void launch_copy(cudaStream_t st, double* dst, const double* src, size_t n);
+
+// ---- gather / split (src/mg_gather.f90) -------------------------------------------------------------------
+// copy the interior of sub-block x (nz, nys, nxs, halo 1) into y (nz, ny, nx, halo 1) at block offset (l,m)
+void launch_gather_place(cudaStream_t st, const double* x, int nzl, int nys, int nxs, double* y, int ny, int nx, int l, int m);
+// y(k,j,i) = x(k, j+m*nys, i+l*nxs), i in 0..nxs+1, j in 0..nys+1
+void launch_split(cudaStream_t st, const double* x, int nzl, int ny, int nx, double* y, int nys, int nxs, int l, int m);
+
+// ---- matrices (src/mg_define_matrix.f90, src/mg_zr_zw.f90) ---------------------------------------------------
+void launch_coarsen2d(cudaStream_t st, const double* f, int nyf, int nxf, double* c, int nyc, int nxc, double w);
+// tab: 4*(nz+1) doubles on the device: cs_r[k], cff_r[k], cs_w[k], cff_w[k]
+void launch_zrzw(cudaStream_t st, const double* h, const double* zeta, const double* tab, double hlim, double* zr, double* zw, int nz, int ny, int nx);
+struct MatrixView {
+  int nx, ny, nz, lev1;
+  const double *dx, *dy, *zr, *zw;
+  double *cw, *dzw, *zxdy, *zydx;
+  double* cA[8];
+  double *bet, *g, *c5b, *c8b, *g1;
+};
+void launch_define_matrix(cudaStream_t st, const MatrixView& M);
+void launch_refresh_derived(cudaStream_t st, const MatrixView& M);   // c5b, c8b, bet, g, g1 from the cA planes
+// max(|c5b|,|c8b|) > 0 ?  result (0/1) written to *flag_dev
+void launch_any_nonzero2(cudaStream_t st, const double* a, const double* b, size_t n, int* flag_dev);
+
+// ---- rhs / correction (src/mg_compute_rhs.f90, src/mg_correct_uvw.f90) ------------------------------------------
+// model layout (i fastest) <-> solver layout (k fastest); src dims: (ni, nj, nk); dst index k + nk*(j + nj*i)
+void launch_transpose_ijk_to_kji(cudaStream_t st, const double* src, double* dst, int ni, int nj, int nk);
+void launch_transpose_kji_to_ijk(cudaStream_t st, const double* src, double* dst, int ni, int nj, int nk);
+struct RhsView {
+  int nx, ny, nz;
+  const double *dx, *dy, *zw, *dzw, *zxdy, *zydx, *cw, *rmask;
+  const double *ut, *vt, *wt;   // k-fastest: ut(nz, ny+2, nx+1) i=1..nx+1 ; vt(nz, ny+1, nx+2) j=1..ny+1 ; wt(nz+1, ny+2, nx+2)
+  double *flux;                 // scratch (nz+1, ny+2, nx+2)
+  double *b;
+  int west_phys, east_phys, south_phys, north_phys;
+};
+void launch_rhs_uf(cudaStream_t st, const RhsView& R);       // flux(k,j,i) = uf, i=1..nx+1, j=1..ny (+ wall zero)
+void launch_rhs_vf(cudaStream_t st, const RhsView& R);
+void launch_rhs_wf(cudaStream_t st, const RhsView& R);
+void launch_rhs_div(cudaStream_t st, const RhsView& R, int dir);   // dir 0: b = d_i uf ; 1: b += d_j vf ; 2: b += d_k wf
+struct CorrView {
+  int nx, ny, nz;
+  const double *dx, *dy, *zr, *zw, *p;
+  double *ut, *vt, *wt;
+};
+void launch_correct_uvw(cudaStream_t st, const CorrView& C);
+
+// ---- layout conversion for accessors -------------------------------------------------------------------------
+void launch_soa_to_aos8(cudaStream_t st, double* const* planes_dev, double* aos, size_t npts);
+void launch_aos8_to_soa(cudaStream_t st, const double* aos, double* const* planes_dev, size_t npts);
+
+}  // namespace mgb

@@ -1,0 +1,593 @@
+// kernels_solve.cu -- FP64 kernels of the per-solve hot path for sm_100a:
+// halo fill, red-black line relaxation (rank-1 corrected), residual + norm, restriction, prolongation.
+// All 3-D fields are (k,j,i) with k fastest and a one-cell halo in j and i.
+// Compiled with -fmad=false so that every expression rounds exactly like the CPU oracle's.
+#include "kernels.cuh"
+
+#include <cstdio>
+
+namespace mgb {
+
+long long g_launches = 0;
+
+#define IDX3(k, j, i, nzl, ny2) ((size_t)(k) + (size_t)(nzl) * ((size_t)(j) + (size_t)(ny2) * (size_t)(i)))
+
+static inline unsigned blocks_for(size_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
+
+// =====================================================================================================
+// generic helpers
+// =====================================================================================================
+__global__ void k_fill(double* __restrict__ a, double v, size_t n) {
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  for (; e < n; e += stride) a[e] = v;
+}
+__global__ void k_copy(double* __restrict__ d, const double* __restrict__ s, size_t n) {
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  for (; e < n; e += stride) d[e] = s[e];
+}
+__global__ void k_axpy_all(double* __restrict__ y, const double* __restrict__ x, size_t n) {
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  for (; e < n; e += stride) y[e] = y[e] + x[e];
+}
+static unsigned capped_blocks(size_t n, unsigned threads) {
+  size_t b = (n + threads - 1) / threads;
+  const size_t cap = 148 * 16;
+  return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+void launch_fill(cudaStream_t st, double* a, double v, size_t n) { if (!n) return; k_fill<<<capped_blocks(n, 256), 256, 0, st>>>(a, v, n); ++g_launches; }
+void launch_copy(cudaStream_t st, double* d, const double* s, size_t n) { if (!n) return; k_copy<<<capped_blocks(n, 256), 256, 0, st>>>(d, s, n); ++g_launches; }
+void launch_axpy_all(cudaStream_t st, double* y, const double* x, size_t n) { if (!n) return; k_axpy_all<<<capped_blocks(n, 256), 256, 0, st>>>(y, x, n); ++g_launches; }
+
+// p += r on the halo ring (j in {0,ny+1} or i in {0,nx+1})
+__global__ void k_add_halo_ring(double* __restrict__ p, const double* __restrict__ r, int nz, int ny, int nx) {
+  const int ny2 = ny + 2;
+  const size_t n_ew = (size_t)2 * ny2 * nz;          // i = 0 and i = nx+1, all j
+  const size_t n_sn = (size_t)2 * nx * nz;           // j = 0 and j = ny+1, i = 1..nx
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n_ew) {
+    int side = (int)(e / ((size_t)ny2 * nz)); size_t rem = e % ((size_t)ny2 * nz);
+    size_t idx = IDX3(0, 0, side ? nx + 1 : 0, nz, ny2) + rem;
+    p[idx] = p[idx] + r[idx];
+  } else if (e < n_ew + n_sn) {
+    e -= n_ew;
+    int side = (int)(e / ((size_t)nx * nz)); size_t rem = e % ((size_t)nx * nz);
+    int i = 1 + (int)(rem / nz), k = (int)(rem % nz);
+    size_t idx = IDX3(k, side ? ny + 1 : 0, i, nz, ny2);
+    p[idx] = p[idx] + r[idx];
+  }
+}
+void launch_add_halo_ring(cudaStream_t st, double* p, const double* r, int nz, int ny, int nx) {
+  size_t n = (size_t)2 * (ny + 2) * nz + (size_t)2 * nx * nz;
+  k_add_halo_ring<<<blocks_for(n, 256), 256, 0, st>>>(p, r, nz, ny, nx); ++g_launches;
+}
+
+// =====================================================================================================
+// halo, nh = 1   (reference: src/mg_mpi_exchange.f90:504-598 for the physical-edge rules)
+// =====================================================================================================
+__global__ void k_halo1_phys(double* __restrict__ a, int nzl, int ny, int nx, Halo1Flags f) {
+  const int ny2 = ny + 2;
+  const size_t n_ew = (size_t)ny * nzl, n_sn = (size_t)nx * nzl;
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < 2 * n_ew) {                       // west (side 0) / east (side 1): j = 1..ny contiguous in memory
+    int side = (int)(e / n_ew); size_t rem = e % n_ew;
+    if (side == 0 && !f.west) a[IDX3(0, 1, 0, nzl, ny2) + rem] = a[IDX3(0, 1, 1, nzl, ny2) + rem];
+    if (side == 1 && !f.east) a[IDX3(0, 1, nx + 1, nzl, ny2) + rem] = a[IDX3(0, 1, nx, nzl, ny2) + rem];
+    return;
+  }
+  e -= 2 * n_ew;
+  if (e < 2 * n_sn) {                       // south (0) / north (1): i = 1..nx
+    int side = (int)(e / n_sn); size_t rem = e % n_sn;
+    int i = 1 + (int)(rem / nzl), k = (int)(rem % nzl);
+    if (side == 0 && !f.south) a[IDX3(k, 0, i, nzl, ny2)] = a[IDX3(k, 1, i, nzl, ny2)];
+    if (side == 1 && !f.north) a[IDX3(k, ny + 1, i, nzl, ny2)] = a[IDX3(k, ny, i, nzl, ny2)];
+    return;
+  }
+  e -= 2 * n_sn;
+  if (e < (size_t)4 * nzl) {                // corners with no neighbour at all on either side: mirror of the interior corner
+    int c = (int)(e / nzl), k = (int)(e % nzl);
+    if (c == 0 && !f.sw && !f.south && !f.west) a[IDX3(k, 0, 0, nzl, ny2)] = a[IDX3(k, 1, 1, nzl, ny2)];
+    if (c == 1 && !f.se && !f.south && !f.east) a[IDX3(k, 0, nx + 1, nzl, ny2)] = a[IDX3(k, 1, nx, nzl, ny2)];
+    if (c == 2 && !f.ne && !f.north && !f.east) a[IDX3(k, ny + 1, nx + 1, nzl, ny2)] = a[IDX3(k, ny, nx, nzl, ny2)];
+    if (c == 3 && !f.nw && !f.north && !f.west) a[IDX3(k, ny + 1, 0, nzl, ny2)] = a[IDX3(k, ny, 1, nzl, ny2)];
+  }
+}
+void launch_halo1_phys(cudaStream_t st, double* a, int nzl, int ny, int nx, Halo1Flags f) {
+  size_t n = (size_t)2 * ny * nzl + (size_t)2 * nx * nzl + (size_t)4 * nzl;
+  k_halo1_phys<<<blocks_for(n, 256), 256, 0, st>>>(a, nzl, ny, nx, f); ++g_launches;
+}
+// corners next to a physical wall but with one lateral neighbour: copy from the halo row/column just received
+__global__ void k_halo1_flagcorners(double* __restrict__ a, int nzl, int ny, int nx, Halo1Flags f) {
+  const int ny2 = ny + 2;
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 4 * nzl) return;
+  int c = e / nzl, k = e % nzl;
+  if (c == 0 && !f.sw) { if (f.south) a[IDX3(k, 0, 0, nzl, ny2)] = a[IDX3(k, 0, 1, nzl, ny2)]; else if (f.west) a[IDX3(k, 0, 0, nzl, ny2)] = a[IDX3(k, 1, 0, nzl, ny2)]; }
+  if (c == 1 && !f.se) { if (f.south) a[IDX3(k, 0, nx + 1, nzl, ny2)] = a[IDX3(k, 0, nx, nzl, ny2)]; else if (f.east) a[IDX3(k, 0, nx + 1, nzl, ny2)] = a[IDX3(k, 1, nx + 1, nzl, ny2)]; }
+  if (c == 2 && !f.ne) { if (f.north) a[IDX3(k, ny + 1, nx + 1, nzl, ny2)] = a[IDX3(k, ny + 1, nx, nzl, ny2)]; else if (f.east) a[IDX3(k, ny + 1, nx + 1, nzl, ny2)] = a[IDX3(k, ny, nx + 1, nzl, ny2)]; }
+  if (c == 3 && !f.nw) { if (f.north) a[IDX3(k, ny + 1, 0, nzl, ny2)] = a[IDX3(k, ny + 1, 1, nzl, ny2)]; else if (f.west) a[IDX3(k, ny + 1, 0, nzl, ny2)] = a[IDX3(k, ny, 0, nzl, ny2)]; }
+}
+void launch_halo1_flagcorners(cudaStream_t st, double* a, int nzl, int ny, int nx, Halo1Flags f) {
+  k_halo1_flagcorners<<<blocks_for((size_t)4 * nzl, 128), 128, 0, st>>>(a, nzl, ny, nx, f); ++g_launches;
+}
+
+// =====================================================================================================
+// halo, nh = 2 (zr, zw)   (reference: src/mg_mpi_exchange.f90:947-1101)
+// array a(nzl, -1:ny+2, -1:nx+2): index k + nzl*((j+1) + (ny+4)*(i+1))
+// =====================================================================================================
+#define IDXH2(k, j, i, nzl, ny4) ((size_t)(k) + (size_t)(nzl) * ((size_t)((j) + 1) + (size_t)(ny4) * (size_t)((i) + 1)))
+__global__ void k_halo2_phys(double* __restrict__ a, int nzl, int ny, int nx, Halo1Flags f) {
+  const int ny4 = ny + 4;
+  const size_t n_ew = (size_t)ny * nzl, n_sn = (size_t)nx * nzl;
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < 2 * n_ew) {
+    int side = (int)(e / n_ew); size_t rem = e % n_ew; int j = 1 + (int)(rem / nzl), k = (int)(rem % nzl);
+    if (side == 0 && !f.west) { double A = a[IDXH2(k, j, 1, nzl, ny4)], B = a[IDXH2(k, j, 2, nzl, ny4)];
+      a[IDXH2(k, j, 0, nzl, ny4)] = A; a[IDXH2(k, j, -1, nzl, ny4)] = 2.0 * A - B; }
+    if (side == 1 && !f.east) { double A = a[IDXH2(k, j, nx, nzl, ny4)], B = a[IDXH2(k, j, nx - 1, nzl, ny4)];
+      a[IDXH2(k, j, nx + 1, nzl, ny4)] = A; a[IDXH2(k, j, nx + 2, nzl, ny4)] = 2.0 * A - B; }
+    return;
+  }
+  e -= 2 * n_ew;
+  if (e < 2 * n_sn) {
+    int side = (int)(e / n_sn); size_t rem = e % n_sn; int i = 1 + (int)(rem / nzl), k = (int)(rem % nzl);
+    if (side == 0 && !f.south) { double A = a[IDXH2(k, 1, i, nzl, ny4)], B = a[IDXH2(k, 2, i, nzl, ny4)];
+      a[IDXH2(k, 0, i, nzl, ny4)] = A; a[IDXH2(k, -1, i, nzl, ny4)] = 2.0 * A - B; }
+    if (side == 1 && !f.north) { double A = a[IDXH2(k, ny, i, nzl, ny4)], B = a[IDXH2(k, ny - 1, i, nzl, ny4)];
+      a[IDXH2(k, ny + 1, i, nzl, ny4)] = A; a[IDXH2(k, ny + 2, i, nzl, ny4)] = 2.0 * A - B; }
+    return;
+  }
+  e -= 2 * n_sn;
+  if (e < (size_t)4 * nzl) {
+    int c = (int)(e / nzl), k = (int)(e % nzl);
+    for (int aa = 1; aa <= 2; ++aa) for (int cc = 1; cc <= 2; ++cc) {
+      if (c == 0 && !f.sw && !f.south && !f.west) a[IDXH2(k, 1 - aa, 1 - cc, nzl, ny4)] = a[IDXH2(k, aa, cc, nzl, ny4)];
+      if (c == 1 && !f.se && !f.south && !f.east) a[IDXH2(k, 1 - aa, nx + cc, nzl, ny4)] = a[IDXH2(k, aa, nx + 1 - cc, nzl, ny4)];
+      if (c == 2 && !f.ne && !f.north && !f.east) a[IDXH2(k, ny + aa, nx + cc, nzl, ny4)] = a[IDXH2(k, ny + 1 - aa, nx + 1 - cc, nzl, ny4)];
+      if (c == 3 && !f.nw && !f.north && !f.west) a[IDXH2(k, ny + aa, 1 - cc, nzl, ny4)] = a[IDXH2(k, ny + 1 - aa, cc, nzl, ny4)];
+    }
+  }
+}
+void launch_halo2_phys(cudaStream_t st, double* a, int nzl, int ny, int nx, Halo1Flags f) {
+  size_t n = (size_t)2 * ny * nzl + (size_t)2 * nx * nzl + (size_t)4 * nzl;
+  k_halo2_phys<<<blocks_for(n, 256), 256, 0, st>>>(a, nzl, ny, nx, f); ++g_launches;
+}
+__global__ void k_halo2_flagcorners(double* __restrict__ a, int nzl, int ny, int nx, Halo1Flags f) {
+  const int ny4 = ny + 4;
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 4 * nzl) return;
+  int c = e / nzl, k = e % nzl;
+  for (int aa = 1; aa <= 2; ++aa) for (int cc = 1; cc <= 2; ++cc) {
+    if (c == 0 && !f.sw) { if (f.south) a[IDXH2(k, 1 - aa, 1 - cc, nzl, ny4)] = a[IDXH2(k, 1 - aa, cc, nzl, ny4)]; else if (f.west) a[IDXH2(k, 1 - aa, 1 - cc, nzl, ny4)] = a[IDXH2(k, aa, 1 - cc, nzl, ny4)]; }
+    if (c == 1 && !f.se) { if (f.south) a[IDXH2(k, 1 - aa, nx + cc, nzl, ny4)] = a[IDXH2(k, 1 - aa, nx + 1 - cc, nzl, ny4)]; else if (f.east) a[IDXH2(k, 1 - aa, nx + cc, nzl, ny4)] = a[IDXH2(k, aa, nx + cc, nzl, ny4)]; }
+    if (c == 2 && !f.ne) { if (f.north) a[IDXH2(k, ny + aa, nx + cc, nzl, ny4)] = a[IDXH2(k, ny + aa, nx + 1 - cc, nzl, ny4)]; else if (f.east) a[IDXH2(k, ny + aa, nx + cc, nzl, ny4)] = a[IDXH2(k, ny + 1 - aa, nx + cc, nzl, ny4)]; }
+    if (c == 3 && !f.nw) { if (f.north) a[IDXH2(k, ny + aa, 1 - cc, nzl, ny4)] = a[IDXH2(k, ny + aa, cc, nzl, ny4)]; else if (f.west) a[IDXH2(k, ny + aa, 1 - cc, nzl, ny4)] = a[IDXH2(k, ny + 1 - aa, 1 - cc, nzl, ny4)]; }
+  }
+}
+void launch_halo2_flagcorners(cudaStream_t st, double* a, int nzl, int ny, int nx, Halo1Flags f) {
+  k_halo2_flagcorners<<<blocks_for((size_t)4 * nzl, 128), 128, 0, st>>>(a, nzl, ny, nx, f); ++g_launches;
+}
+
+// pack a rectangular (j0..j0+nrows-1) x (i0..i0+ncols-1) patch of an array with halo width nh into a dense buffer
+// buf(k, jr, ic), k fastest  -- used for S/N faces and corners of the inter-GPU exchange
+__global__ void k_pack_rows(const double* __restrict__ a, double* __restrict__ buf, int nzl, int nyh, int nh, int j0, int nrows, int i0, int ncols) {
+  size_t n = (size_t)nzl * nrows * ncols;
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  int k = (int)(e % nzl); size_t t = e / nzl; int jr = (int)(t % nrows), ic = (int)(t / nrows);
+  buf[e] = a[(size_t)k + (size_t)nzl * ((size_t)(j0 + jr - 1 + nh) + (size_t)nyh * (size_t)(i0 + ic - 1 + nh))];
+}
+__global__ void k_unpack_rows(double* __restrict__ a, const double* __restrict__ buf, int nzl, int nyh, int nh, int j0, int nrows, int i0, int ncols) {
+  size_t n = (size_t)nzl * nrows * ncols;
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  int k = (int)(e % nzl); size_t t = e / nzl; int jr = (int)(t % nrows), ic = (int)(t / nrows);
+  a[(size_t)k + (size_t)nzl * ((size_t)(j0 + jr - 1 + nh) + (size_t)nyh * (size_t)(i0 + ic - 1 + nh))] = buf[e];
+}
+// j0,i0 are Fortran indices (may be <= 0 for halo cells); nyh = ny + 2*nh
+void launch_pack_rows(cudaStream_t st, const double* a, double* buf, int nzl, int ny, int nx, int nh, int j0, int nrows, int i0, int ncols) {
+  size_t n = (size_t)nzl * nrows * ncols; (void)nx;
+  k_pack_rows<<<blocks_for(n, 256), 256, 0, st>>>(a, buf, nzl, ny + 2 * nh, nh, j0, nrows, i0, ncols); ++g_launches;
+}
+void launch_unpack_rows(cudaStream_t st, double* a, const double* buf, int nzl, int ny, int nx, int nh, int j0, int nrows, int i0, int ncols) {
+  size_t n = (size_t)nzl * nrows * ncols; (void)nx;
+  k_unpack_rows<<<blocks_for(n, 256), 256, 0, st>>>(a, buf, nzl, ny + 2 * nh, nh, j0, nrows, i0, ncols); ++g_launches;
+}
+
+// =====================================================================================================
+// relaxation
+// =====================================================================================================
+// x1(j,i) = p(1,j,i) for every column incl. halo: snapshot of the bottom plane taken before a colour is updated
+__global__ void k_snapshot_x1(const double* __restrict__ p, double* __restrict__ x1, int nz, size_t ncols) {
+  size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < ncols) x1[c] = p[c * nz];
+}
+void launch_snapshot_x1(cudaStream_t st, const LevelView& L) {
+  size_t ncols = (size_t)(L.ny + 2) * (L.nx + 2);
+  k_snapshot_x1<<<blocks_for(ncols, 256), 256, 0, st>>>(L.p, L.x1, L.nz, ncols); ++g_launches;
+}
+
+__device__ __forceinline__ int colour_jstart(const ColourSet& cs, int i) { return cs.jrule == 0 ? 1 + ((i + cs.rb) & 1) : cs.jfix; }
+
+// Kernel A: for every column of the colour build the right-hand side of the vertical tridiagonal system
+// (k-parallel, coalesced along k), solve it by Thomas (one thread per column out of shared memory), write p.
+//   tile = TI consecutive visited i  x  TJ consecutive colour-columns in j ; TC = TI*TJ columns per CTA
+//   dynamic smem: 3 arrays [TC][nz+1] : rhs/x, bet, ud
+// Thomas recurrences (src/mg_relax.f90:308-334) with the pivots' reciprocals `bet` precomputed at matrix time:
+//   x(1) = rhs(1)*bet(1) ; x(k) = (rhs(k) - ud(k-1)*x(k-1))*bet(k) ; back: x(k) -= (ud(k)*bet(k))*x(k+1)
+__global__ void __launch_bounds__(256) k_relax_A(LevelView L, ColourSet cs, int TI, int TJ, int ntj) {
+  extern __shared__ double sm[];
+  const int nz = L.nz, ny2 = L.ny + 2, pitch = nz + 1;
+  const int TC = TI * TJ;
+  double* s_rhs = sm;
+  double* s_bet = sm + (size_t)TC * pitch;
+  double* s_ud = s_bet + (size_t)TC * pitch;
+  const int tile_j = blockIdx.x % ntj, tile_i = blockIdx.x / ntj;
+  const int sj = nz;                       // stride of j
+  const size_t si = (size_t)nz * ny2;      // stride of i
+  const double* __restrict__ p = L.p;
+  const double* __restrict__ b = L.b;
+  const double* __restrict__ c2 = L.cA[1]; const double* __restrict__ c3 = L.cA[2]; const double* __restrict__ c4 = L.cA[3];
+  const double* __restrict__ c5 = L.cA[4]; const double* __restrict__ c6 = L.cA[5]; const double* __restrict__ c7 = L.cA[6];
+  const double* __restrict__ c8 = L.cA[7]; const double* __restrict__ bet = L.bet;
+
+  // ---- phase 1: rhs, coalesced along k
+  const int nelem = TC * nz;
+  for (int e = threadIdx.x; e < nelem; e += blockDim.x) {
+    const int k = e % nz, c = e / nz;
+    const int ci = c / TJ, cj = c % TJ;
+    const int i = cs.istart + (tile_i * TI + ci) * cs.istep;
+    if (i > L.nx) continue;
+    const int j = colour_jstart(cs, i) + 2 * (tile_j * TJ + cj);
+    if (j > L.ny) continue;
+    const size_t idx = IDX3(k, j, i, nz, ny2);
+    double acc = b[idx];
+    if (k < nz - 1) acc = acc - c3[idx] * p[idx - sj + 1];
+    if (k > 0)      acc = acc - c3[idx + sj - 1] * p[idx + sj - 1];
+    acc = acc - c4[idx] * p[idx - sj];
+    acc = acc - c4[idx + sj] * p[idx + sj];
+    if (k > 0)      acc = acc - c5[idx] * p[idx - sj - 1];
+    if (k < nz - 1) acc = acc - c5[idx + sj + 1] * p[idx + sj + 1];
+    if (k < nz - 1) acc = acc - c6[idx] * p[idx - si + 1];
+    if (k > 0)      acc = acc - c6[idx + si - 1] * p[idx + si - 1];
+    acc = acc - c7[idx] * p[idx - si];
+    acc = acc - c7[idx + si] * p[idx + si];
+    if (k > 0)      acc = acc - c8[idx] * p[idx - si - 1];
+    if (k < nz - 1) acc = acc - c8[idx + si + 1] * p[idx + si + 1];
+    if (k == 0) {
+      if (cs.bottom_mode == 1) {          // rank-1 form: only the two not-yet-updated (i+1) neighbours, from the snapshot
+        const size_t c2d = (size_t)j + (size_t)ny2 * i;
+        acc = acc - L.c5b[c2d - 1 + ny2] * L.x1[c2d - 1 + ny2];
+        acc = acc - L.c8b[c2d + 1 + ny2] * L.x1[c2d + 1 + ny2];
+      } else if (cs.bottom_mode == 2) {   // all four bottom-diagonal terms from p (src/mg_relax.f90:271-276)
+        acc = acc - c5[idx] * p[idx + sj - si];
+        acc = acc - c5[idx - sj + si] * p[idx - sj + si];
+        acc = acc - c8[idx] * p[idx - sj - si];
+        acc = acc - c8[idx + sj + si] * p[idx + sj + si];
+      }
+    }
+    s_rhs[c * pitch + k] = acc;
+    s_bet[c * pitch + k] = bet[idx];
+    s_ud[c * pitch + k] = (k < nz - 1) ? c2[idx + 1] : 0.0;
+  }
+  __syncthreads();
+
+  // ---- phase 2: Thomas, one thread per column
+  for (int c = threadIdx.x; c < TC; c += blockDim.x) {
+    const int ci = c / TJ, cj = c % TJ;
+    const int i = cs.istart + (tile_i * TI + ci) * cs.istep;
+    if (i > L.nx) continue;
+    const int j = colour_jstart(cs, i) + 2 * (tile_j * TJ + cj);
+    if (j > L.ny) continue;
+    double* x = s_rhs + c * pitch;
+    const double* bt = s_bet + c * pitch;
+    const double* ud = s_ud + c * pitch;
+    double xm = x[0] * bt[0];
+    x[0] = xm;
+    for (int k = 1; k < nz; ++k) { xm = (x[k] - ud[k - 1] * xm) * bt[k]; x[k] = xm; }
+    for (int k = nz - 2; k >= 0; --k) { xm = x[k] - (ud[k] * bt[k]) * xm; x[k] = xm; }
+    if (cs.bottom_mode == 1) L.q1[(size_t)j + (size_t)ny2 * i] = xm;
+  }
+  __syncthreads();
+
+  // ---- phase 3: write back, coalesced along k
+  double* __restrict__ pw = L.p;
+  for (int e = threadIdx.x; e < nelem; e += blockDim.x) {
+    const int k = e % nz, c = e / nz;
+    const int ci = c / TJ, cj = c % TJ;
+    const int i = cs.istart + (tile_i * TI + ci) * cs.istep;
+    if (i > L.nx) continue;
+    const int j = colour_jstart(cs, i) + 2 * (tile_j * TJ + cj);
+    if (j > L.ny) continue;
+    pw[IDX3(k, j, i, nz, ny2)] = s_rhs[c * pitch + k];
+  }
+}
+
+static void relax_tiling(const LevelView& L, const ColourSet& cs, int& TI, int& TJ, int& nti, int& ntj, size_t& smem) {
+  const int nyc = (L.ny + 1) / 2;                    // colour columns per visited i (upper bound)
+  const int nvi = (L.nx - cs.istart) / cs.istep + 1; // visited i
+  int tc_max = 4096 / L.nz;                          // columns per CTA: aim at ~4096 points per tile
+  if (tc_max < 32) tc_max = 32;
+  if (tc_max > 1024) tc_max = 1024;
+  while (tc_max > 1 && (size_t)tc_max * (L.nz + 1) * 3 * sizeof(double) > 56 * 1024) tc_max /= 2;
+  TJ = nyc < tc_max ? nyc : tc_max;
+  TI = tc_max / TJ; if (TI < 1) TI = 1; if (TI > nvi) TI = nvi;
+  ntj = (nyc + TJ - 1) / TJ; nti = (nvi + TI - 1) / TI;
+  smem = (size_t)TI * TJ * (L.nz + 1) * 3 * sizeof(double);
+}
+void launch_relax_A(cudaStream_t st, const LevelView& L, const ColourSet& cs) {
+  int TI, TJ, nti, ntj; size_t smem;
+  relax_tiling(L, cs, TI, TJ, nti, ntj, smem);
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(k_relax_A, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+  k_relax_A<<<nti * ntj, 256, smem, st>>>(L, cs, TI, TJ, ntj); ++g_launches;
+}
+
+// Kernel B: the sequential part of the red-black bottom coupling, on the 2-D k=1 plane only.
+// For i ascending: s(j,i) = -(c5b(j,i) x1(j+1,i-1) + c8b(j,i) x1(j-1,i-1)) ; x1(j,i) = q1(j,i) + s(j,i) g1(j,i)
+// One CTA; the previous column of x1 lives in shared memory (two ping-pong rows).
+__global__ void __launch_bounds__(1024) k_relax_B(LevelView L, ColourSet cs) {
+  extern __shared__ double sm[];
+  const int ny = L.ny, nx = L.nx, ny2 = ny + 2;
+  double* row0 = sm;            // x1(:, i-1)
+  double* row1 = sm + ny2;      // x1(:, i)
+  for (int j = threadIdx.x; j < ny2; j += blockDim.x) row0[j] = L.x1[j];          // column i = 0 (halo, old values)
+  __syncthreads();
+  double* prev = row0; double* cur = row1;
+  for (int i = 1; i <= nx; ++i) {
+    const int js = colour_jstart(cs, i);
+    const size_t col = (size_t)ny2 * i;
+    // entries of column i that are not updated by this colour keep their old value (other colour, halo rows)
+    for (int j = threadIdx.x; j < ny2; j += blockDim.x) {
+      const bool mine = (j >= js) && (j <= ny) && (((j - js) & 1) == 0);
+      double v;
+      if (mine) {
+        const double sv = -(L.c5b[col + j] * prev[j + 1] + L.c8b[col + j] * prev[j - 1]);
+        v = L.q1[col + j] + sv * L.g1[col + j];
+        L.s[col + j] = sv;
+        L.x1[col + j] = v;
+      } else {
+        v = L.x1[col + j];
+      }
+      cur[j] = v;
+    }
+    __syncthreads();
+    double* t = prev; prev = cur; cur = t;
+  }
+}
+void launch_relax_B(cudaStream_t st, const LevelView& L, const ColourSet& cs) {
+  int threads = 32; while (threads < L.ny + 2 && threads < 1024) threads *= 2;
+  size_t smem = (size_t)2 * (L.ny + 2) * sizeof(double);
+  k_relax_B<<<1, threads, smem, st>>>(L, cs); ++g_launches;
+}
+
+// Kernel C: p(:,j,i) += s(j,i) * g(:,j,i) on the columns of the colour
+__global__ void __launch_bounds__(256) k_relax_C(LevelView L, ColourSet cs, int nyc) {
+  const int nz = L.nz, ny2 = L.ny + 2;
+  // one i per blockIdx.y ; x dimension covers (k, colour column)
+  const int i = cs.istart + blockIdx.y * cs.istep;
+  const int js = colour_jstart(cs, i);
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nyc * nz) return;
+  const int k = e % nz, jc = e / nz;
+  const int j = js + 2 * jc;
+  if (j > L.ny) return;
+  const double sv = L.s[(size_t)j + (size_t)ny2 * i];
+  const size_t idx = IDX3(k, j, i, nz, ny2);
+  L.p[idx] = L.p[idx] + sv * L.g[idx];
+}
+void launch_relax_C(cudaStream_t st, const LevelView& L, const ColourSet& cs) {
+  const int nyc = (L.ny + 1) / 2;
+  const int nvi = (L.nx - cs.istart) / cs.istep + 1;
+  dim3 grid(blocks_for((size_t)nyc * L.nz, 256), nvi);
+  k_relax_C<<<grid, 256, 0, st>>>(L, cs, nyc); ++g_launches;
+}
+
+// =====================================================================================================
+// residual + norm   (src/mg_relax.f90:421-515)
+// =====================================================================================================
+__device__ __forceinline__ double block_sum_256(double v, double* s_red) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) s_red[w] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x < 32) {
+    t = (threadIdx.x < (blockDim.x >> 5)) ? s_red[threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+  }
+  return t;   // valid in thread 0
+}
+
+// one block handles a chunk of one i-slab: elements (k, j) flattened, j = 1..ny
+__global__ void __launch_bounds__(256) k_residual(LevelView L, int real_matrix, int chunks_per_i, double* __restrict__ partials) {
+  __shared__ double s_red[8];
+  const int nz = L.nz, ny = L.ny, ny2 = ny + 2;
+  const int i = 1 + blockIdx.x / chunks_per_i, chunk = blockIdx.x % chunks_per_i;
+  const int sj = nz; const size_t si = (size_t)nz * ny2;
+  const double* __restrict__ p = L.p; const double* __restrict__ b = L.b;
+  const double* __restrict__ c1 = L.cA[0]; const double* __restrict__ c2 = L.cA[1]; const double* __restrict__ c3 = L.cA[2];
+  const double* __restrict__ c4 = L.cA[3]; const double* __restrict__ c5 = L.cA[4]; const double* __restrict__ c6 = L.cA[5];
+  const double* __restrict__ c7 = L.cA[6]; const double* __restrict__ c8 = L.cA[7];
+  double* __restrict__ r = L.r;
+  const int nelem = ny * nz;
+  const int per_chunk = (nelem + chunks_per_i - 1) / chunks_per_i;
+  const int e0 = chunk * per_chunk, e1 = min(nelem, e0 + per_chunk);
+  double sum = 0.0;
+  for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+    const int k = e % nz, j = 1 + e / nz;
+    const size_t idx = IDX3(k, j, i, nz, ny2);
+    double acc = b[idx];
+    acc = acc - c1[idx] * p[idx];
+    if (k > 0)      acc = acc - c2[idx] * p[idx - 1];
+    if (k < nz - 1) acc = acc - c2[idx + 1] * p[idx + 1];
+    if (k < nz - 1) acc = acc - c3[idx] * p[idx - sj + 1];
+    if (k > 0)      acc = acc - c3[idx + sj - 1] * p[idx + sj - 1];
+    acc = acc - c4[idx] * p[idx - sj];
+    acc = acc - c4[idx + sj] * p[idx + sj];
+    if (k > 0)      acc = acc - c5[idx] * p[idx - sj - 1];
+    if (k < nz - 1) acc = acc - c5[idx + sj + 1] * p[idx + sj + 1];
+    if (k < nz - 1) acc = acc - c6[idx] * p[idx - si + 1];
+    if (k > 0)      acc = acc - c6[idx + si - 1] * p[idx + si - 1];
+    acc = acc - c7[idx] * p[idx - si];
+    acc = acc - c7[idx + si] * p[idx + si];
+    if (k > 0)      acc = acc - c8[idx] * p[idx - si - 1];
+    if (k < nz - 1) acc = acc - c8[idx + si + 1] * p[idx + si + 1];
+    if (k == 0 && real_matrix) {
+      acc = acc - c5[idx] * p[idx + sj - si];
+      acc = acc - c5[idx - sj + si] * p[idx - sj + si];
+      acc = acc - c8[idx] * p[idx - sj - si];
+      acc = acc - c8[idx + sj + si] * p[idx + sj + si];
+    }
+    r[idx] = acc;
+    sum += acc * acc;
+  }
+  const double t = block_sum_256(sum, s_red);
+  if (threadIdx.x == 0) partials[blockIdx.x] = t;
+}
+// fixed-order final reduction (deterministic): one block
+__global__ void __launch_bounds__(256) k_reduce_final(const double* __restrict__ partials, int n, double* __restrict__ out) {
+  __shared__ double s_red[8];
+  double v = 0.0;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) v += partials[e];
+  const double t = block_sum_256(v, s_red);
+  if (threadIdx.x == 0) *out = t;
+}
+static int residual_chunks(const LevelView& L) {
+  const int nelem = L.ny * L.nz;
+  int chunks = (nelem + 4095) / 4096;        // <= 16 elements per thread
+  return chunks < 1 ? 1 : chunks;
+}
+int residual_num_partials(const LevelView& L) { return L.nx * residual_chunks(L); }
+void launch_residual(cudaStream_t st, const LevelView& L, int real_matrix, double* partials, double* sum_out) {
+  const int chunks = residual_chunks(L);
+  k_residual<<<L.nx * chunks, 256, 0, st>>>(L, real_matrix, chunks, partials); ++g_launches;
+  k_reduce_final<<<1, 256, 0, st>>>(partials, L.nx * chunks, sum_out); ++g_launches;
+}
+__global__ void __launch_bounds__(256) k_sumsq(const double* __restrict__ a, int nz, int ny, int chunks_per_i, double* __restrict__ partials) {
+  __shared__ double s_red[8];
+  const int ny2 = ny + 2;
+  const int i = 1 + blockIdx.x / chunks_per_i, chunk = blockIdx.x % chunks_per_i;
+  const int nelem = ny * nz;
+  const int per_chunk = (nelem + chunks_per_i - 1) / chunks_per_i;
+  const int e0 = chunk * per_chunk, e1 = min(nelem, e0 + per_chunk);
+  double sum = 0.0;
+  for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) { const double v = a[IDX3(0, 1, i, nz, ny2) + e]; sum += v * v; }
+  const double t = block_sum_256(sum, s_red);
+  if (threadIdx.x == 0) partials[blockIdx.x] = t;
+}
+void launch_sumsq(cudaStream_t st, const LevelView& L, const double* a, double* partials, double* sum_out) {
+  const int chunks = residual_chunks(L);
+  k_sumsq<<<L.nx * chunks, 256, 0, st>>>(a, L.nz, L.ny, chunks, partials); ++g_launches;
+  k_reduce_final<<<1, 256, 0, st>>>(partials, L.nx * chunks, sum_out); ++g_launches;
+}
+
+// =====================================================================================================
+// intergrid transfers
+// =====================================================================================================
+// restriction: y(k2,j2,i2) = sum of the 8 fine cells (src/mg_intergrids.f90:149-160), same summation order
+__global__ void __launch_bounds__(256) k_restrict8(const double* __restrict__ xf, int nzf, int nyf, double* __restrict__ yc, int nzc, int nyc, int nxc) {
+  const size_t n = (size_t)nzc * nyc * nxc;
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const int k2 = (int)(e % nzc); size_t t = e / nzc; const int j2 = 1 + (int)(t % nyc), i2 = 1 + (int)(t / nyc);
+  const int k = 2 * k2, j = 2 * j2 - 1, i = 2 * i2 - 1;       // k 0-based
+  const int nyf2 = nyf + 2;
+  const size_t f00 = IDX3(k, j, i, nzf, nyf2), sj = nzf, si = (size_t)nzf * nyf2;
+  const double2 a = *reinterpret_cast<const double2*>(xf + f00);             // (k, k+1) at (j, i)
+  const double2 b = *reinterpret_cast<const double2*>(xf + f00 + si);        // (j, i+1)
+  const double2 c = *reinterpret_cast<const double2*>(xf + f00 + sj);        // (j+1, i)
+  const double2 d = *reinterpret_cast<const double2*>(xf + f00 + sj + si);   // (j+1, i+1)
+  double z = a.x + b.x + c.x + d.x + a.y + b.y + c.y + d.y;
+  yc[IDX3(k2, j2, i2, nzc, nyc + 2)] = z;
+}
+void launch_restrict8(cudaStream_t st, const double* xf, int nzf, int nyf, int nxf, double* yc, int nzc, int nyc, int nxc) {
+  (void)nxf;
+  size_t n = (size_t)nzc * nyc * nxc;
+  k_restrict8<<<blocks_for(n, 256), 256, 0, st>>>(xf, nzf, nyf, yc, nzc, nyc, nxc); ++g_launches;
+}
+
+// prolongation (src/mg_intergrids.f90:366-450 linear, :336-363 nearest); thread per fine interior point
+__global__ void __launch_bounds__(256) k_prolong(const double* __restrict__ xc, int nzc, int nyc, int nxc,
+                                                double* __restrict__ rf, double* __restrict__ pf, int linear, int mode) {
+  const int nzf = 2 * nzc, nyf = 2 * nyc, nxf = 2 * nxc;
+  const size_t n = (size_t)nzf * nyf * nxf;
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const int kf = (int)(e % nzf); size_t t = e / nzf; const int jf = 1 + (int)(t % nyf), i_f = 1 + (int)(t / nyf);
+  const int K = kf + 1;                                   // Fortran k
+  const int j2 = (jf + 1) / 2, i2 = (i_f + 1) / 2;
+  const int dj = (jf & 1) ? -1 : +1, di = (i_f & 1) ? -1 : +1;   // odd fine index -> neighbour below, even -> above
+  const int nyc2 = nyc + 2;
+  double v;
+  if (!linear) {
+    v = xc[IDX3((K + 1) / 2 - 1, j2, i2, nzc, nyc2)];
+  } else {
+    const double a = 9.0 / 16.0, b = 3.0 / 16.0, c = 1.0 / 16.0, d = 27.0 / 64.0, ee = 9.0 / 64.0, f = 3.0 / 64.0, g = 1.0 / 64.0;
+    if (K == 1 || K == nzf) {
+      const int k2 = (K == 1) ? 0 : nzc - 1;
+      const size_t o = IDX3(k2, j2, i2, nzc, nyc2);
+      const double x00 = xc[o], xdd = xc[IDX3(k2, j2 + dj, i2 + di, nzc, nyc2)], xd0 = xc[IDX3(k2, j2 + dj, i2, nzc, nyc2)], x0d = xc[IDX3(k2, j2, i2 + di, nzc, nyc2)];
+      v = a * x00 + c * xdd + b * xd0 + b * x0d;
+      if (K == nzf) v = 0.5 * v;
+    } else {
+      const int k2 = (K + 1) / 2, kp = k2 - ((K % 2) * 2 - 1);      // Fortran indices
+      const double x00 = xc[IDX3(k2 - 1, j2, i2, nzc, nyc2)], xdd = xc[IDX3(k2 - 1, j2 + dj, i2 + di, nzc, nyc2)];
+      const double xd0 = xc[IDX3(k2 - 1, j2 + dj, i2, nzc, nyc2)], x0d = xc[IDX3(k2 - 1, j2, i2 + di, nzc, nyc2)];
+      const double y00 = xc[IDX3(kp - 1, j2, i2, nzc, nyc2)], ydd = xc[IDX3(kp - 1, j2 + dj, i2 + di, nzc, nyc2)];
+      const double yd0 = xc[IDX3(kp - 1, j2 + dj, i2, nzc, nyc2)], y0d = xc[IDX3(kp - 1, j2, i2 + di, nzc, nyc2)];
+      v = d * x00 + f * xdd + ee * xd0 + ee * x0d + ee * y00 + g * ydd + f * yd0 + f * y0d;
+    }
+  }
+  const size_t of = IDX3(kf, jf, i_f, nzf, nyf + 2);
+  if (mode == 0) rf[of] = v; else pf[of] = pf[of] + v;
+}
+void launch_prolong(cudaStream_t st, const double* xc, int nzc, int nyc, int nxc, double* rf, double* pf, int linear, int mode) {
+  size_t n = (size_t)8 * nzc * nyc * nxc;
+  k_prolong<<<blocks_for(n, 256), 256, 0, st>>>(xc, nzc, nyc, nxc, rf, pf, linear, mode); ++g_launches;
+}
+
+// =====================================================================================================
+// gather / split
+// =====================================================================================================
+__global__ void k_gather_place(const double* __restrict__ x, int nzl, int nys, int nxs, double* __restrict__ y, int ny, int l, int m) {
+  size_t n = (size_t)nzl * nys * nxs;
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  int k = (int)(e % nzl); size_t t = e / nzl; int j = 1 + (int)(t % nys), i = 1 + (int)(t / nys);
+  y[IDX3(k, j + m * nys, i + l * nxs, nzl, ny + 2)] = x[IDX3(k, j, i, nzl, nys + 2)];
+}
+void launch_gather_place(cudaStream_t st, const double* x, int nzl, int nys, int nxs, double* y, int ny, int nx, int l, int m) {
+  (void)nx; size_t n = (size_t)nzl * nys * nxs;
+  k_gather_place<<<blocks_for(n, 256), 256, 0, st>>>(x, nzl, nys, nxs, y, ny, l, m); ++g_launches;
+}
+__global__ void k_split(const double* __restrict__ x, int nzl, int ny, double* __restrict__ y, int nys, int nxs, int l, int m) {
+  size_t n = (size_t)nzl * (nys + 2) * (nxs + 2);
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  int k = (int)(e % nzl); size_t t = e / nzl; int j = (int)(t % (nys + 2)), i = (int)(t / (nys + 2));
+  y[e] = x[IDX3(k, j + m * nys, i + l * nxs, nzl, ny + 2)];
+}
+void launch_split(cudaStream_t st, const double* x, int nzl, int ny, int nx, double* y, int nys, int nxs, int l, int m) {
+  (void)nx; size_t n = (size_t)nzl * (nys + 2) * (nxs + 2);
+  k_split<<<blocks_for(n, 256), 256, 0, st>>>(x, nzl, ny, y, nys, nxs, l, m); ++g_launches;
+}
+
+// =====================================================================================================
+// cA layout conversion for the accessors (AoS of the reference <-> device SoA planes)
+// =====================================================================================================
+__global__ void k_soa_to_aos8(double* const* __restrict__ planes, double* __restrict__ aos, size_t npts) {
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  for (; e < npts * 8; e += stride) aos[e] = planes[e & 7][e >> 3];
+}
+__global__ void k_aos8_to_soa(const double* __restrict__ aos, double* const* __restrict__ planes, size_t npts) {
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  for (; e < npts * 8; e += stride) planes[e & 7][e >> 3] = aos[e];
+}
+void launch_soa_to_aos8(cudaStream_t st, double* const* planes_dev, double* aos, size_t npts) {
+  k_soa_to_aos8<<<capped_blocks(npts * 8, 256), 256, 0, st>>>(planes_dev, aos, npts); ++g_launches;
+}
+void launch_aos8_to_soa(cudaStream_t st, const double* aos, double* const* planes_dev, size_t npts) {
+  k_aos8_to_soa<<<capped_blocks(npts * 8, 256), 256, 0, st>>>(aos, planes_dev, npts); ++g_launches;
+}
+
+}  // namespace mgb

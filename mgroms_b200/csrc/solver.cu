@@ -1,0 +1,792 @@
+// solver.cu -- state, level hierarchy on the device, multigrid cycles, inter-GPU exchange and the C ABI
+// (include/mgb.h) of libmgb.  One solver instance per process, one GPU per process.
+#include "../../include/mgb.h"
+#include "kernels.cuh"
+#include "mgb_internal.h"
+
+#include <cuda_runtime.h>
+#include <nccl.h>
+#include <dlfcn.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace mgb {
+
+// ------------------------------------------------------------------------------------------------------
+// error handling
+// ------------------------------------------------------------------------------------------------------
+static std::string g_err;
+static int fail(const std::string& m) { g_err = m; return 1; }
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+#define RC(call) do { int r_ = (call); if (r_ != 0) return r_; } while (0)
+
+// ------------------------------------------------------------------------------------------------------
+// NCCL, loaded lazily so that single-GPU use has no dependency on it
+// ------------------------------------------------------------------------------------------------------
+struct NcclApi {
+  void* h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load() {
+  if (g_nccl.h) return 0;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) { g_nccl.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (g_nccl.h) break; }
+  if (!g_nccl.h) return fail(std::string("cannot load libnccl: ") + dlerror());
+#define SYM(field, name) *(void**)(&g_nccl.field) = dlsym(g_nccl.h, name); if (!g_nccl.field) return fail(std::string("libnccl lacks ") + name)
+  SYM(GetUniqueId, "ncclGetUniqueId"); SYM(CommInitRank, "ncclCommInitRank"); SYM(CommDestroy, "ncclCommDestroy");
+  SYM(Send, "ncclSend"); SYM(Recv, "ncclRecv"); SYM(AllReduce, "ncclAllReduce");
+  SYM(GroupStart, "ncclGroupStart"); SYM(GroupEnd, "ncclGroupEnd"); SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+  return 0;
+}
+#define NC(call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) return fail(std::string(#call) + ": " + g_nccl.GetErrorString(r_)); } while (0)
+
+// ------------------------------------------------------------------------------------------------------
+// state
+// ------------------------------------------------------------------------------------------------------
+struct Level {
+  LevelDims d;
+  LevelView v{};
+  double *dx = nullptr, *dy = nullptr, *zeta = nullptr, *h = nullptr, *zr = nullptr, *zw = nullptr, *cw = nullptr;
+  double *dzw = nullptr, *zxdy = nullptr, *zydx = nullptr;   // level 1 only
+  double *dummy3 = nullptr, *gatherbuf = nullptr;             // gathered levels only
+  double *sub2d[4] = {nullptr, nullptr, nullptr, nullptr};    // coarse geometry before gathering
+  double *tab = nullptr;
+  double** planes_dev = nullptr;
+  double *packS = nullptr, *packN = nullptr, *unpS = nullptr, *unpN = nullptr;   // S/N face staging (multi-GPU)
+  double *pack8[8] = {nullptr}, *unp8[8] = {nullptr};         // nh=2 staging (setup)
+  double *partials = nullptr; int npartials = 0;
+  Halo1Flags hf{};
+  bool bottom_diag = true;
+  size_t n3() const { return (size_t)d.nz * (d.ny + 2) * (d.nx + 2); }
+  size_t n2() const { return (size_t)(d.ny + 2) * (d.nx + 2); }
+};
+
+struct Solver {
+  bool inited = false, have_matrices = false;
+  Params P;
+  int rank = 0, npx = 1, npy = 1, nranks = 1, device = 0;
+  std::vector<Level> L;              // L[lev-1]
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  ncclComm_t comm = nullptr;
+  double hlim = 0, theta_b = 0, theta_s = 0;
+  // level-1 model arrays (k fastest) and staging for the (i,j,k) host layout
+  double *ut = nullptr, *vt = nullptr, *wt = nullptr, *stage = nullptr, *flux = nullptr, *rmask = nullptr;
+  double *sums = nullptr;            // device scalars: [0] residual sum, [1] bnorm sum, [2] all-reduced
+  int* flag_dev = nullptr;
+  std::vector<void*> allocs;
+  std::vector<double> hist_res, hist_conv;
+  double last_ms = 0; int last_iters = 0;
+  bool fused_prolong = true;
+  int nlevs() const { return (int)L.size(); }
+};
+static Solver S;
+static Params g_params;              // defaults + mgb_set_param overrides (used by mgb_plan_levels)
+static std::vector<std::pair<std::string, std::string>> g_overrides;   // applied after the namelist file in mgb_init
+static std::vector<LevelDims> g_plan;
+
+static int dalloc(double** p, size_t n) {
+  void* q = nullptr;
+  if (n == 0) n = 1;
+  CU(cudaMalloc(&q, n * sizeof(double)));
+  CU(cudaMemsetAsync(q, 0, n * sizeof(double), S.st));
+  S.allocs.push_back(q);
+  *p = (double*)q;
+  return 0;
+}
+
+static Halo1Flags flags_of(const LevelDims& d) {
+  Halo1Flags f;
+  f.south = d.neighb[0] >= 0; f.east = d.neighb[1] >= 0; f.north = d.neighb[2] >= 0; f.west = d.neighb[3] >= 0;
+  f.sw = d.neighb[4] >= 0; f.se = d.neighb[5] >= 0; f.ne = d.neighb[6] >= 0; f.nw = d.neighb[7] >= 0;
+  return f;
+}
+
+static int check_level(int lev) {
+  if (!S.inited) return fail("mgb_init has not been called");
+  if (lev < 1 || lev > S.nlevs()) return fail("level out of range");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// halo fill  (fill_halo, src/mg_mpi_exchange.f90).  nh = 1 or 2; nzl = levels of the array.
+// ------------------------------------------------------------------------------------------------------
+static int exchange(Level& g, double* a, int nzl, int nh) {
+  // inter-GPU part: what Isend/Irecv + unpack do.  Order of directions = S,E,N,W,SW,SE,NE,NW
+  const int nx = g.d.nx, ny = g.d.ny;
+  const int nyh = ny + 2 * nh;
+  auto at = [&](int j, int i) { return a + (size_t)nzl * ((size_t)(j - 1 + nh) + (size_t)nyh * (size_t)(i - 1 + nh)); };
+  // send patches (Fortran j0,i0,rows,cols) and recv patches per direction
+  struct Patch { int j0, nr, i0, nc; };
+  const Patch sendp[8] = {{1, nh, 1, nx}, {1, ny, nx - nh + 1, nh}, {ny - nh + 1, nh, 1, nx}, {1, ny, 1, nh},
+                          {1, nh, 1, nh}, {1, nh, nx - nh + 1, nh}, {ny - nh + 1, nh, nx - nh + 1, nh}, {ny - nh + 1, nh, 1, nh}};
+  const Patch recvp[8] = {{1 - nh, nh, 1, nx}, {1, ny, nx + 1, nh}, {ny + 1, nh, 1, nx}, {1, ny, 1 - nh, nh},
+                          {1 - nh, nh, 1 - nh, nh}, {1 - nh, nh, nx + 1, nh}, {ny + 1, nh, nx + 1, nh}, {ny + 1, nh, 1 - nh, nh}};
+  // a patch is contiguous in memory when it spans whole columns' j-range of width 1 ... simple rule: nc == 1 && rows contiguous
+  auto contiguous = [&](const Patch& p) { return p.nc == 1 || (p.j0 == 1 - nh && p.nr == nyh); };
+  for (int q = 0; q < 8; ++q) {
+    if (g.d.neighb[q] < 0) continue;
+    if (!contiguous(sendp[q])) launch_pack_rows(S.st, a, g.pack8[q], nzl, ny, nx, nh, sendp[q].j0, sendp[q].nr, sendp[q].i0, sendp[q].nc);
+  }
+  NC(g_nccl.GroupStart());
+  for (int q = 0; q < 8; ++q) {
+    const int peer = g.d.neighb[q];
+    if (peer < 0) continue;
+    const size_t cnt = (size_t)nzl * sendp[q].nr * sendp[q].nc;
+    const double* sb = contiguous(sendp[q]) ? at(sendp[q].j0, sendp[q].i0) : g.pack8[q];
+    double* rb = contiguous(recvp[q]) ? at(recvp[q].j0, recvp[q].i0) : g.unp8[q];
+    NC(g_nccl.Send(sb, cnt, ncclDouble, peer, S.comm, S.st));
+    NC(g_nccl.Recv(rb, cnt, ncclDouble, peer, S.comm, S.st));
+  }
+  NC(g_nccl.GroupEnd());
+  for (int q = 0; q < 8; ++q) {
+    if (g.d.neighb[q] < 0) continue;
+    if (!contiguous(recvp[q])) launch_unpack_rows(S.st, a, g.unp8[q], nzl, ny, nx, nh, recvp[q].j0, recvp[q].nr, recvp[q].i0, recvp[q].nc);
+  }
+  return 0;
+}
+
+static int fill_halo(int lev, double* a, int nzl, int nh) {
+  Level& g = S.L[lev - 1];
+  if (nh == 1) launch_halo1_phys(S.st, a, nzl, g.d.ny, g.d.nx, g.hf); else launch_halo2_phys(S.st, a, nzl, g.d.ny, g.d.nx, g.hf);
+  bool any = false; for (int q = 0; q < 8; ++q) any |= g.d.neighb[q] >= 0;
+  if (any) {
+    if (!S.comm) return fail("multi-rank level but mgb_comm_init has not been called");
+    RC(exchange(g, a, nzl, nh));
+    if (nh == 1) launch_halo1_flagcorners(S.st, a, nzl, g.d.ny, g.d.nx, g.hf); else launch_halo2_flagcorners(S.st, a, nzl, g.d.ny, g.d.nx, g.hf);
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// gather / split  (src/mg_gather.f90)
+// ------------------------------------------------------------------------------------------------------
+// x: my sub-block (nzl, nys+2, nxs+2) ; y: gathered array (nzl, ny+2, nx+2) of level lev
+static int gather(int lev, const double* x, double* y, int nzl) {
+  Level& g = S.L[lev - 1];
+  const int nxs = g.d.nx / g.d.ngx, nys = g.d.ny / g.d.ngy;
+  const size_t Ng = (size_t)nzl * (nys + 2) * (nxs + 2);
+  if (!S.comm) return fail("gather needs mgb_comm_init");
+  NC(g_nccl.GroupStart());
+  for (int q = 0; q < g.d.nmembers; ++q) {
+    const int peer = g.d.members[q];
+    if (peer == S.rank) continue;
+    NC(g_nccl.Send(x, Ng, ncclDouble, peer, S.comm, S.st));
+    NC(g_nccl.Recv(g.gatherbuf + (size_t)q * (size_t)g.d.nz * (nys + 2) * (nxs + 2), Ng, ncclDouble, peer, S.comm, S.st));
+  }
+  NC(g_nccl.GroupEnd());
+  for (int q = 0; q < g.d.nmembers; ++q) {
+    const int l = q % g.d.ngx, m = q / g.d.ngx;
+    const double* src = (g.d.members[q] == S.rank) ? x : g.gatherbuf + (size_t)q * (size_t)g.d.nz * (nys + 2) * (nxs + 2);
+    launch_gather_place(S.st, src, nzl, nys, nxs, y, g.d.ny, g.d.nx, l, m);
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// operators
+// ------------------------------------------------------------------------------------------------------
+static int relax(int lev, int nsweeps) {
+  Level& g = S.L[lev - 1];
+  const std::string& m = S.P.relax_method;
+  const bool real_matrix = (S.P.cmatrix == "real");
+  if (m == "Red-Black" || m == "RB") {
+    for (int it = 0; it < nsweeps; ++it)
+      for (int rb = 1; rb <= 2; ++rb) {
+        ColourSet cs{1, 1, 0, rb, 0, 0};
+        const bool rank1 = real_matrix && g.bottom_diag;
+        cs.bottom_mode = rank1 ? 1 : 0;
+        if (rank1) launch_snapshot_x1(S.st, g.v);
+        launch_relax_A(S.st, g.v, cs);
+        if (rank1) { launch_relax_B(S.st, g.v, cs); launch_relax_C(S.st, g.v, cs); }
+        RC(fill_halo(lev, g.v.p, g.d.nz, 1));
+      }
+  } else if (m == "Four-Color" || m == "FC") {
+    for (int it = 0; it < nsweeps; ++it)
+      for (int fc1 = 1; fc1 <= 2; ++fc1) for (int fc2 = 1; fc2 <= 2; ++fc2) {
+        ColourSet cs{1 + (fc1 - 1) % 2, 2, 1, 0, 1 + (fc2 - 1) % 2, real_matrix ? 2 : 0};
+        if (cs.istart <= g.d.nx && cs.jfix <= g.d.ny) launch_relax_A(S.st, g.v, cs);
+        RC(fill_halo(lev, g.v.p, g.d.nz, 1));
+      }
+  } else {
+    return fail("relax_method '" + m + "' is not built (RB and FC are; GS is listed under SURVEY 8f-4)");
+  }
+  return 0;
+}
+
+// r = b - A p, halo(r); the sum of squares of this rank is left in S.sums[0]
+static int residual(int lev) {
+  Level& g = S.L[lev - 1];
+  launch_residual(S.st, g.v, S.P.cmatrix == "real", g.partials, S.sums);
+  RC(fill_halo(lev, g.v.r, g.d.nz, 1));
+  return 0;
+}
+// global_sum (src/mg_mpi_exchange.f90:1555-1571): all-reduce + rescale for gathered levels; returns host value
+static int global_sum(int lev, const double* dev_local, double* out) {
+  double v = 0.0;
+  if (S.nranks > 1) {
+    if (!S.comm) return fail("global_sum needs mgb_comm_init");
+    NC(g_nccl.AllReduce(dev_local, S.sums + 2, 1, ncclDouble, ncclSum, S.comm, S.st));
+    CU(cudaMemcpyAsync(&v, S.sums + 2, sizeof(double), cudaMemcpyDeviceToHost, S.st));
+  } else {
+    CU(cudaMemcpyAsync(&v, dev_local, sizeof(double), cudaMemcpyDeviceToHost, S.st));
+  }
+  CU(cudaStreamSynchronize(S.st));
+  const LevelDims& d = S.L[lev - 1].d; const LevelDims& d1 = S.L[0].d;
+  *out = v * (d.npx * d.npy) / (d1.npx * d1.npy);
+  return 0;
+}
+
+static int fine2coarse(int lev, bool copy_b_to_r) {
+  Level& f = S.L[lev - 1]; Level& c = S.L[lev];
+  const int nxs = c.d.nx / c.d.ngx, nys = c.d.ny / c.d.ngy;
+  double* target = c.d.gather ? c.dummy3 : c.v.b;
+  launch_restrict8(S.st, f.v.r, f.d.nz, f.d.ny, f.d.nx, target, c.d.nz, nys, nxs);
+  if (c.d.gather) RC(gather(lev + 1, c.dummy3, c.v.b, c.d.nz));
+  RC(fill_halo(lev + 1, c.v.b, c.d.nz, 1));
+  launch_fill(S.st, c.v.p, 0.0, c.n3());
+  if (copy_b_to_r) launch_copy(S.st, c.v.r, c.v.b, c.n3());      // Fcycle: grid(lev+1)%r = grid(lev+1)%b
+  return 0;
+}
+
+static int coarse2fine(int lev, bool fused) {
+  Level& f = S.L[lev - 1]; Level& c = S.L[lev];
+  const double* pc = c.v.p; int nxc = c.d.nx, nyc = c.d.ny;
+  if (c.d.gather) {
+    nxc = c.d.nx / c.d.ngx; nyc = c.d.ny / c.d.ngy;
+    launch_split(S.st, c.v.p, c.d.nz, c.d.ny, c.d.nx, c.dummy3, nyc, nxc, c.d.key % 2, c.d.key / 2);
+    pc = c.dummy3;
+  }
+  const int linear = (S.P.interp_type == "linear");
+  if (fused) {   // p_f += P p_c on the interior, then refresh halo(p_f): identical to the reference whenever halo(p_f) was consistent
+    launch_prolong(S.st, pc, c.d.nz, nyc, nxc, f.v.r, f.v.p, linear, 1);
+    RC(fill_halo(lev, f.v.p, f.d.nz, 1));
+  } else {       // the reference's sequence: r_f = P p_c ; halo(r_f) ; p_f += r_f everywhere
+    launch_prolong(S.st, pc, c.d.nz, nyc, nxc, f.v.r, f.v.p, linear, 0);
+    RC(fill_halo(lev, f.v.r, f.d.nz, 1));
+    launch_axpy_all(S.st, f.v.p, f.v.r, f.n3());
+  }
+  return 0;
+}
+
+static int vcycle(int lev1) {
+  const int Ln = S.nlevs();
+  for (int lev = lev1; lev <= Ln - 1; ++lev) { RC(relax(lev, S.P.ns_pre)); RC(residual(lev)); RC(fine2coarse(lev, false)); }
+  RC(relax(Ln, S.P.ns_coarsest));
+  for (int lev = Ln - 1; lev >= lev1; --lev) { RC(coarse2fine(lev, S.fused_prolong)); RC(relax(lev, S.P.ns_post)); }
+  return 0;
+}
+static int fcycle() {
+  const int Ln = S.nlevs();
+  for (int lev = 1; lev <= Ln - 1; ++lev) RC(fine2coarse(lev, true));
+  RC(relax(Ln, S.P.ns_coarsest));
+  for (int lev = Ln - 1; lev >= 1; --lev) { RC(coarse2fine(lev, S.fused_prolong)); RC(vcycle(lev)); }
+  return 0;
+}
+
+static int solve_p() {
+  if (!S.have_matrices) return fail("mgb_matrices has not been called");
+  Level& g = S.L[0];
+  const double tol = S.P.solver_prec; const int maxite = S.P.solver_maxiter;
+  launch_fill(S.st, g.v.p, 0.0, g.n3());
+  CU(cudaEventRecord(S.ev0, S.st));
+  int nite = 0;
+  launch_sumsq(S.st, g.v, g.v.b, g.partials, S.sums + 1);
+  double bsum = 0, rsum = 0;
+  RC(global_sum(1, S.sums + 1, &bsum));
+  const double bnorm = std::sqrt(bsum);
+  RC(residual(1)); RC(global_sum(1, S.sums, &rsum));
+  double rnorm = std::sqrt(rsum);
+  double res0 = rnorm / bnorm;
+  S.hist_res.assign(1, res0); S.hist_conv.assign(1, 0.0);
+  while (nite < maxite && res0 > tol) {
+    RC(fcycle());
+    RC(residual(1)); RC(global_sum(1, S.sums, &rsum));
+    rnorm = std::sqrt(rsum) / bnorm;
+    const double conv = res0 / rnorm;
+    res0 = rnorm;
+    ++nite;
+    S.hist_res.push_back(rnorm); S.hist_conv.push_back(conv);
+  }
+  CU(cudaEventRecord(S.ev1, S.st));
+  CU(cudaEventSynchronize(S.ev1));
+  float ms = 0; CU(cudaEventElapsedTime(&ms, S.ev0, S.ev1));
+  S.last_ms = ms; S.last_iters = nite;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// matrices
+// ------------------------------------------------------------------------------------------------------
+static void vertical_tables(int nz, double hlim, double theta_b, double theta_s, std::vector<double>& tab) {
+  // k-only part of src/mg_zr_zw.f90:112-166 (same expressions, host libm): cs_r, cff_r (k=1..nz), cs_w, cff_w (k=1..nz+1)
+  const int nzp = nz + 1; tab.assign((size_t)4 * nzp, 0.0);
+  const double cff = 1.0 / (double)nz;
+  for (int k = 1; k <= nzp; ++k) {
+    const double sc_w = cff * (double)(k - 1 - nz);
+    const double cswf = (theta_s > 0.0) ? (1.0 - std::cosh(theta_s * sc_w)) / (std::cosh(theta_s) - 1.0) : -(sc_w * sc_w);
+    const double cs_w = (theta_b > 0.0) ? (std::exp(theta_b * cswf) - 1.0) / (1.0 - std::exp(-theta_b)) : cswf;
+    tab[2 * nzp + k - 1] = cs_w; tab[3 * nzp + k - 1] = hlim * sc_w;
+    if (k <= nz) {
+      const double sc_r = cff * ((double)(k - nz) - 0.5);
+      const double csrf = (theta_s > 0.0) ? (1.0 - std::cosh(theta_s * sc_r)) / (std::cosh(theta_s) - 1.0) : -(sc_r * sc_r);
+      const double cs_r = (theta_b > 0.0) ? (std::exp(theta_b * csrf) - 1.0) / (1.0 - std::exp(-theta_b)) : csrf;
+      tab[k - 1] = cs_r; tab[nzp + k - 1] = hlim * sc_r;
+    }
+  }
+}
+
+static MatrixView matrix_view(Level& g, int lev) {
+  MatrixView M{};
+  M.nx = g.d.nx; M.ny = g.d.ny; M.nz = g.d.nz; M.lev1 = (lev == 1);
+  M.dx = g.dx; M.dy = g.dy; M.zr = g.zr; M.zw = g.zw; M.cw = g.cw; M.dzw = g.dzw; M.zxdy = g.zxdy; M.zydx = g.zydx;
+  for (int q = 0; q < 8; ++q) M.cA[q] = g.v.cA[q];
+  M.bet = g.v.bet; M.g = g.v.g; M.c5b = g.v.c5b; M.c8b = g.v.c8b; M.g1 = g.v.g1;
+  return M;
+}
+
+static int define_matrices() {
+  for (int lev = 1; lev <= S.nlevs(); ++lev) {
+    Level& g = S.L[lev - 1];
+    if (lev > 1) {
+      Level& f = S.L[lev - 2];
+      const int nxs = g.d.nx / g.d.ngx, nys = g.d.ny / g.d.ngy;
+      double* dst[4] = {g.dx, g.dy, g.zeta, g.h};
+      const double* src[4] = {f.dx, f.dy, f.zeta, f.h};
+      const double w[4] = {0.5, 0.5, 0.25, 0.25};
+      for (int q = 0; q < 4; ++q) {
+        double* t = g.d.gather ? g.sub2d[q] : dst[q];
+        launch_coarsen2d(S.st, src[q], f.d.ny, f.d.nx, t, nys, nxs, w[q]);
+        if (g.d.gather) RC(gather(lev, t, dst[q], 1));
+      }
+    }
+    RC(fill_halo(lev, g.dx, 1, 1)); RC(fill_halo(lev, g.dy, 1, 1)); RC(fill_halo(lev, g.zeta, 1, 1)); RC(fill_halo(lev, g.h, 1, 1));
+    std::vector<double> tab; vertical_tables(g.d.nz, S.hlim, S.theta_b, S.theta_s, tab);
+    CU(cudaMemcpyAsync(g.tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, S.st));
+    CU(cudaStreamSynchronize(S.st));   // tab is a stack temporary
+    launch_zrzw(S.st, g.h, g.zeta, g.tab, S.hlim, g.zr, g.zw, g.d.nz, g.d.ny, g.d.nx);
+    RC(fill_halo(lev, g.zr, g.d.nz, 2)); RC(fill_halo(lev, g.zw, g.d.nz + 1, 2));
+    for (int q = 0; q < 8; ++q) launch_fill(S.st, g.v.cA[q], 0.0, g.n3());
+    launch_fill(S.st, g.v.c5b, 0.0, g.n2()); launch_fill(S.st, g.v.c8b, 0.0, g.n2());
+    launch_define_matrix(S.st, matrix_view(g, lev));
+    launch_any_nonzero2(S.st, g.v.c5b, g.v.c8b, g.n2(), S.flag_dev);
+    int flag = 1;
+    CU(cudaMemcpyAsync(&flag, S.flag_dev, sizeof(int), cudaMemcpyDeviceToHost, S.st));
+    CU(cudaStreamSynchronize(S.st));
+    g.bottom_diag = flag != 0;
+  }
+  CU(cudaStreamSynchronize(S.st));
+  S.have_matrices = true;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// rhs / correction with host (model-layout) arrays
+// ------------------------------------------------------------------------------------------------------
+static size_t n_u() { const LevelDims& d = S.L[0].d; return (size_t)(d.nx + 1) * (d.ny + 2) * d.nz; }
+static size_t n_v() { const LevelDims& d = S.L[0].d; return (size_t)(d.nx + 2) * (d.ny + 1) * d.nz; }
+static size_t n_w() { const LevelDims& d = S.L[0].d; return (size_t)(d.nx + 2) * (d.ny + 2) * (d.nz + 1); }
+
+static int upload_uvw(const double* u, const double* v, const double* w) {
+  const LevelDims& d = S.L[0].d;
+  CU(cudaMemcpyAsync(S.stage, u, n_u() * sizeof(double), cudaMemcpyHostToDevice, S.st));
+  launch_transpose_ijk_to_kji(S.st, S.stage, S.ut, d.nx + 1, d.ny + 2, d.nz);
+  CU(cudaMemcpyAsync(S.stage, v, n_v() * sizeof(double), cudaMemcpyHostToDevice, S.st));
+  launch_transpose_ijk_to_kji(S.st, S.stage, S.vt, d.nx + 2, d.ny + 1, d.nz);
+  CU(cudaMemcpyAsync(S.stage, w, n_w() * sizeof(double), cudaMemcpyHostToDevice, S.st));
+  launch_transpose_ijk_to_kji(S.st, S.stage, S.wt, d.nx + 2, d.ny + 2, d.nz + 1);
+  return 0;
+}
+static int download_uvw(double* u, double* v, double* w) {
+  const LevelDims& d = S.L[0].d;
+  launch_transpose_kji_to_ijk(S.st, S.ut, S.stage, d.nx + 1, d.ny + 2, d.nz);
+  CU(cudaMemcpyAsync(u, S.stage, n_u() * sizeof(double), cudaMemcpyDeviceToHost, S.st));
+  launch_transpose_kji_to_ijk(S.st, S.vt, S.stage, d.nx + 2, d.ny + 1, d.nz);
+  CU(cudaMemcpyAsync(v, S.stage, n_v() * sizeof(double), cudaMemcpyDeviceToHost, S.st));
+  launch_transpose_kji_to_ijk(S.st, S.wt, S.stage, d.nx + 2, d.ny + 2, d.nz + 1);
+  CU(cudaMemcpyAsync(w, S.stage, n_w() * sizeof(double), cudaMemcpyDeviceToHost, S.st));
+  CU(cudaStreamSynchronize(S.st));
+  return 0;
+}
+
+// exchange of one flux face with the neighbour (what fill_halo(...,lbc_null) does where a neighbour exists):
+// dir 'u': my flux(:,1:ny,nx+1) <- east's flux(:,1:ny,1) ; dir 'v': my flux(:,ny+1,1:nx) <- north's flux(:,1,1:nx)
+static int exchange_flux_face(char dir) {
+  Level& g = S.L[0]; const int nx = g.d.nx, ny = g.d.ny, nz = g.d.nz;
+  const int east = g.d.neighb[1], west = g.d.neighb[3], north = g.d.neighb[2], south = g.d.neighb[0];
+  auto at = [&](int j, int i) { return S.flux + (size_t)nz * ((size_t)j + (size_t)(ny + 2) * i); };
+  if (dir == 'u') {
+    if (east < 0 && west < 0) return 0;
+    NC(g_nccl.GroupStart());
+    if (west >= 0) NC(g_nccl.Send(at(1, 1), (size_t)nz * ny, ncclDouble, west, S.comm, S.st));
+    if (east >= 0) NC(g_nccl.Recv(at(1, nx + 1), (size_t)nz * ny, ncclDouble, east, S.comm, S.st));
+    NC(g_nccl.GroupEnd());
+  } else {
+    if (north < 0 && south < 0) return 0;
+    if (south >= 0) launch_pack_rows(S.st, S.flux, g.pack8[0], nz, ny, nx, 1, 1, 1, 1, nx);
+    NC(g_nccl.GroupStart());
+    if (south >= 0) NC(g_nccl.Send(g.pack8[0], (size_t)nz * nx, ncclDouble, south, S.comm, S.st));
+    if (north >= 0) NC(g_nccl.Recv(g.unp8[2], (size_t)nz * nx, ncclDouble, north, S.comm, S.st));
+    NC(g_nccl.GroupEnd());
+    if (north >= 0) launch_unpack_rows(S.st, S.flux, g.unp8[2], nz, ny, nx, 1, ny + 1, 1, 1, nx);
+  }
+  return 0;
+}
+
+static int compute_rhs_device() {
+  Level& g = S.L[0];
+  RhsView R{};
+  R.nx = g.d.nx; R.ny = g.d.ny; R.nz = g.d.nz;
+  R.dx = g.dx; R.dy = g.dy; R.zw = g.zw; R.dzw = g.dzw; R.zxdy = g.zxdy; R.zydx = g.zydx; R.cw = g.cw; R.rmask = S.rmask;
+  R.ut = S.ut; R.vt = S.vt; R.wt = S.wt; R.flux = S.flux; R.b = g.v.b;
+  R.west_phys = !g.hf.west; R.east_phys = !g.hf.east; R.south_phys = !g.hf.south; R.north_phys = !g.hf.north;
+  launch_fill(S.st, g.v.b, 0.0, g.n3());                      // rhs(:,:,:) = zero  (src/mg_compute_rhs.f90:91)
+  launch_rhs_uf(S.st, R); if (S.nranks > 1) RC(exchange_flux_face('u')); launch_rhs_div(S.st, R, 0);
+  launch_rhs_vf(S.st, R); if (S.nranks > 1) RC(exchange_flux_face('v')); launch_rhs_div(S.st, R, 1);
+  launch_rhs_wf(S.st, R); launch_rhs_div(S.st, R, 2);
+  return 0;
+}
+static int set_rmask(const double* rmask) {
+  Level& g = S.L[0];
+  if (rmask) CU(cudaMemcpyAsync(S.rmask, rmask, g.n2() * sizeof(double), cudaMemcpyHostToDevice, S.st));
+  else launch_fill(S.st, S.rmask, 1.0, g.n2());
+  return 0;
+}
+static int correct_uvw_device() {
+  Level& g = S.L[0];
+  CorrView C{g.d.nx, g.d.ny, g.d.nz, g.dx, g.dy, g.zr, g.zw, g.v.p, S.ut, S.vt, S.wt};
+  launch_correct_uvw(S.st, C);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// init / clean
+// ------------------------------------------------------------------------------------------------------
+static int clean() {
+  if (S.st) cudaStreamSynchronize(S.st);
+  for (void* p : S.allocs) cudaFree(p);
+  S.allocs.clear();
+  if (S.comm && g_nccl.CommDestroy) { g_nccl.CommDestroy(S.comm); }
+  if (S.ev0) cudaEventDestroy(S.ev0);
+  if (S.ev1) cudaEventDestroy(S.ev1);
+  if (S.st) cudaStreamDestroy(S.st);
+  S = Solver();
+  return 0;
+}
+
+static int init(int nx, int ny, int nz, int npx, int npy, int rank, const char* namelist_path, int device) {
+  if (S.inited) clean();
+  S.P = Params();
+  std::string msg;
+  const char* path = (namelist_path && namelist_path[0]) ? namelist_path : "nh_namelist";
+  int rc = namelist_read(path, S.P, msg);
+  if (rc < 0) return fail(msg);
+  for (auto& kv : g_overrides) if (namelist_set(S.P, kv.first.c_str(), kv.second.c_str(), msg) != 0) return fail(msg);
+  std::vector<LevelDims> plan;
+  if (plan_levels(S.P, nx, ny, nz, npx, npy, rank, plan, msg) != 0) return fail(msg);
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0) return fail(std::string("no usable CUDA device (libmgb has no CPU fallback): ") + cudaGetErrorString(ce));
+  if (device >= 0) CU(cudaSetDevice(device));
+  CU(cudaGetDevice(&S.device));
+  S.rank = rank; S.npx = npx; S.npy = npy; S.nranks = npx * npy;
+  CU(cudaStreamCreateWithFlags(&S.st, cudaStreamNonBlocking));
+  CU(cudaEventCreate(&S.ev0)); CU(cudaEventCreate(&S.ev1));
+  S.L.resize(plan.size());
+  for (size_t q = 0; q < plan.size(); ++q) {
+    Level& g = S.L[q]; g.d = plan[q]; g.hf = flags_of(g.d);
+    const LevelDims& d = g.d; const int lev = (int)q + 1;
+    const size_t n3 = g.n3(), n2 = g.n2();
+    g.v.nx = d.nx; g.v.ny = d.ny; g.v.nz = d.nz;
+    RC(dalloc(&g.v.p, n3)); RC(dalloc(&g.v.b, n3)); RC(dalloc(&g.v.r, n3));
+    for (int c = 0; c < 8; ++c) RC(dalloc(&g.v.cA[c], n3));
+    RC(dalloc(&g.v.bet, n3)); RC(dalloc(&g.v.g, n3));
+    RC(dalloc(&g.v.c5b, n2)); RC(dalloc(&g.v.c8b, n2)); RC(dalloc(&g.v.g1, n2)); RC(dalloc(&g.v.q1, n2)); RC(dalloc(&g.v.x1, n2)); RC(dalloc(&g.v.s, n2));
+    RC(dalloc(&g.dx, n2)); RC(dalloc(&g.dy, n2)); RC(dalloc(&g.zeta, n2)); RC(dalloc(&g.h, n2));
+    RC(dalloc(&g.zr, (size_t)d.nz * (d.ny + 4) * (d.nx + 4))); RC(dalloc(&g.zw, (size_t)(d.nz + 1) * (d.ny + 4) * (d.nx + 4)));
+    RC(dalloc(&g.cw, (size_t)(d.nz + 1) * n2));
+    RC(dalloc(&g.tab, (size_t)4 * (d.nz + 1)));
+    if (lev == 1) { RC(dalloc(&g.dzw, (size_t)(d.nz + 1) * n2)); RC(dalloc(&g.zxdy, n3)); RC(dalloc(&g.zydx, n3)); }
+    g.npartials = residual_num_partials(g.v);
+    RC(dalloc(&g.partials, (size_t)g.npartials));
+    { void* pp = nullptr; CU(cudaMalloc(&pp, 8 * sizeof(double*))); S.allocs.push_back(pp); g.planes_dev = (double**)pp;
+      CU(cudaMemcpy(g.planes_dev, g.v.cA, 8 * sizeof(double*), cudaMemcpyHostToDevice)); }
+    if (d.gather) {
+      const int nxs = d.nx / d.ngx, nys = d.ny / d.ngy;
+      RC(dalloc(&g.dummy3, (size_t)d.nz * (nys + 2) * (nxs + 2)));
+      RC(dalloc(&g.gatherbuf, (size_t)4 * d.nz * (nys + 2) * (nxs + 2)));
+      for (int c = 0; c < 4; ++c) RC(dalloc(&g.sub2d[c], (size_t)(nys + 2) * (nxs + 2)));
+    }
+    bool any = false; for (int c = 0; c < 8; ++c) any |= d.neighb[c] >= 0;
+    if (any) {   // staging for strided faces: sized for nh = 2 and nz+1 levels
+      const size_t face = (size_t)2 * (d.nz + 1) * (size_t)(std::max(d.nx, d.ny) + 4);
+      for (int c = 0; c < 8; ++c) { RC(dalloc(&g.pack8[c], face)); RC(dalloc(&g.unp8[c], face)); }
+    }
+  }
+  { const LevelDims& d = S.L[0].d;
+    RC(dalloc(&S.ut, (size_t)(d.nx + 1) * (d.ny + 2) * d.nz)); RC(dalloc(&S.vt, (size_t)(d.nx + 2) * (d.ny + 1) * d.nz));
+    RC(dalloc(&S.wt, (size_t)(d.nx + 2) * (d.ny + 2) * (d.nz + 1))); RC(dalloc(&S.stage, (size_t)(d.nx + 2) * (d.ny + 2) * (d.nz + 1)));
+    RC(dalloc(&S.flux, (size_t)(d.nx + 2) * (d.ny + 2) * (d.nz + 1))); RC(dalloc(&S.rmask, (size_t)(d.nx + 2) * (d.ny + 2)));
+    RC(dalloc(&S.sums, 8));
+    void* fp = nullptr; CU(cudaMalloc(&fp, sizeof(int))); S.allocs.push_back(fp); S.flag_dev = (int*)fp; }
+  const char* ex = std::getenv("MGB_EXACT_STATE");
+  S.fused_prolong = !(ex && ex[0] == '1');
+  CU(cudaStreamSynchronize(S.st));
+  S.inited = true;
+  g_plan = plan;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// field access
+// ------------------------------------------------------------------------------------------------------
+struct FieldRef { double* ptr; size_t n; bool is_cA; };
+static int field_ref(int lev, const std::string& name, FieldRef& out) {
+  Level& g = S.L[lev - 1]; const LevelDims& d = g.d;
+  const size_t n3 = g.n3(), n2 = g.n2();
+  out.is_cA = false;
+  if (name == "p") out = {g.v.p, n3, false}; else if (name == "b") out = {g.v.b, n3, false}; else if (name == "r") out = {g.v.r, n3, false};
+  else if (name == "cA") out = {nullptr, 8 * n3, true};
+  else if (name == "dx") out = {g.dx, n2, false}; else if (name == "dy") out = {g.dy, n2, false};
+  else if (name == "zeta") out = {g.zeta, n2, false}; else if (name == "h") out = {g.h, n2, false};
+  else if (name == "zr") out = {g.zr, (size_t)d.nz * (d.ny + 4) * (d.nx + 4), false};
+  else if (name == "zw") out = {g.zw, (size_t)(d.nz + 1) * (d.ny + 4) * (d.nx + 4), false};
+  else if (name == "cw") out = {g.cw, (size_t)(d.nz + 1) * n2, false};
+  else if (name == "dzw" && lev == 1) out = {g.dzw, (size_t)(d.nz + 1) * n2, false};
+  else if (name == "zxdy" && lev == 1) out = {g.zxdy, n3, false};
+  else if (name == "zydx" && lev == 1) out = {g.zydx, n3, false};
+  else if (name == "bet") out = {g.v.bet, n3, false}; else if (name == "g") out = {g.v.g, n3, false};
+  else if (name == "s") out = {g.v.s, n2, false}; else if (name == "x1") out = {g.v.x1, n2, false}; else if (name == "q1") out = {g.v.q1, n2, false};
+  else if (name == "dummy3" && d.gather) out = {g.dummy3, (size_t)d.nz * (d.ny / d.ngy + 2) * (d.nx / d.ngx + 2), false};
+  else return fail("unknown field '" + name + "'");
+  return 0;
+}
+
+}  // namespace mgb
+
+// =========================================================================================================
+// C ABI
+// =========================================================================================================
+using namespace mgb;
+
+extern "C" {
+
+const char* mgb_last_error(void) { return g_err.c_str(); }
+const char* mgb_version(void) { return "mgroms_b200 0.1 (sm_100a, FP64, -fmad=false)"; }
+
+int mgb_set_param(const char* key, const char* value) {
+  std::string m; if (namelist_set(g_params, key, value, m) != 0) return fail(m);
+  g_overrides.push_back({key, value}); return 0;
+}
+int mgb_reset_params(void) { g_params = Params(); g_overrides.clear(); return 0; }
+
+int mgb_plan_levels(int nx, int ny, int nz, int npx, int npy, int rank) {
+  std::string m; Params P = g_params;
+  if (plan_levels(P, nx, ny, nz, npx, npy, rank, g_plan, m) != 0) return fail(m);
+  return 0;
+}
+int mgb_nlevs(void) { return (int)g_plan.size(); }
+int mgb_level_info(int lev, int* info) {
+  if (lev < 1 || lev > (int)g_plan.size()) return fail("level out of range");
+  const LevelDims& d = g_plan[lev - 1];
+  const int v[12] = {d.nx, d.ny, d.nz, d.npx, d.npy, d.incx, d.incy, d.gather, d.ngx, d.ngy, d.key, d.color};
+  for (int q = 0; q < 12; ++q) info[q] = v[q];
+  for (int q = 0; q < 8; ++q) info[12 + q] = d.neighb[q];
+  return 0;
+}
+int mgb_gather_members(int lev, int* out4) {
+  if (lev < 1 || lev > (int)g_plan.size()) return -1;
+  const LevelDims& d = g_plan[lev - 1];
+  for (int q = 0; q < d.nmembers; ++q) out4[q] = d.members[q];
+  return d.nmembers;
+}
+
+int mgb_init(int nx, int ny, int nz, int npx, int npy, int rank, const char* namelist_path, int device) {
+  return init(nx, ny, nz, npx, npy, rank, namelist_path, device);
+}
+int mgb_clean(void) { return clean(); }
+
+int mgb_comm_unique_id(void* id128) {
+  RC(nccl_load());
+  ncclUniqueId id; NC(g_nccl.GetUniqueId(&id));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  std::memcpy(id128, &id, 128);
+  return 0;
+}
+int mgb_comm_init(const void* id128) {
+  if (!S.inited) return fail("mgb_init first");
+  RC(nccl_load());
+  ncclUniqueId id; std::memcpy(&id, id128, 128);
+  NC(g_nccl.CommInitRank(&S.comm, S.nranks, id, S.rank));
+  return 0;
+}
+
+int mgb_matrices(const double* dx, const double* dy, const double* zeta, const double* h, const double* rmask,
+                 double hc, double theta_b, double theta_s) {
+  if (!S.inited) return fail("mgb_init has not been called");
+  Level& g = S.L[0]; const size_t n2 = g.n2() * sizeof(double);
+  S.hlim = hc; S.theta_b = theta_b; S.theta_s = theta_s;
+  CU(cudaMemcpyAsync(g.dx, dx, n2, cudaMemcpyHostToDevice, S.st)); CU(cudaMemcpyAsync(g.dy, dy, n2, cudaMemcpyHostToDevice, S.st));
+  CU(cudaMemcpyAsync(g.zeta, zeta, n2, cudaMemcpyHostToDevice, S.st)); CU(cudaMemcpyAsync(g.h, h, n2, cudaMemcpyHostToDevice, S.st));
+  RC(set_rmask(rmask));
+  CU(cudaStreamSynchronize(S.st));
+  return define_matrices();
+}
+
+int mgb_compute_rhs(const double* rmask, const double* u, const double* v, const double* w) {
+  if (!S.have_matrices) return fail("mgb_matrices has not been called");
+  RC(set_rmask(rmask)); RC(upload_uvw(u, v, w)); RC(compute_rhs_device());
+  CU(cudaStreamSynchronize(S.st));
+  return 0;
+}
+int mgb_check_nondivergence(const double* rmask, const double* u, const double* v, const double* w) { return mgb_compute_rhs(rmask, u, v, w); }
+int mgb_solve_p(void) { if (!S.inited) return fail("mgb_init has not been called"); return solve_p(); }
+int mgb_correct_uvw(double* u, double* v, double* w) {
+  if (!S.have_matrices) return fail("mgb_matrices has not been called");
+  RC(correct_uvw_device()); return download_uvw(u, v, w);
+}
+int mgb_solve(const double* rmask, double* u, double* v, double* w) {
+  if (!S.have_matrices) return fail("mgb_matrices has not been called");
+  RC(set_rmask(rmask)); RC(upload_uvw(u, v, w)); RC(compute_rhs_device());
+  RC(solve_p());
+  RC(correct_uvw_device()); return download_uvw(u, v, w);
+}
+
+int mgb_get_history(double* res, double* conv, int cap) {
+  const int n = (int)S.hist_res.size();
+  for (int q = 0; q < n && q < cap; ++q) { res[q] = S.hist_res[q]; if (conv) conv[q] = S.hist_conv[q]; }
+  return n;
+}
+int mgb_write_fort100(const char* path) {
+  FILE* f = std::fopen(path, "w"); if (!f) return fail("cannot open fort.100 target");
+  for (size_t q = 0; q < S.hist_res.size(); ++q) {
+    if (q == 0) std::fprintf(f, "  %24.16E %11d\n", S.hist_res[0], 0);
+    else std::fprintf(f, "  %24.16E  %24.16E\n", S.hist_res[q], S.hist_conv[q]);
+  }
+  std::fclose(f); return 0;
+}
+double mgb_last_solve_ms(void) { return S.last_ms; }
+int mgb_last_solve_iters(void) { return S.last_iters; }
+
+int mgb_relax(int lev, int nsweeps) { RC(check_level(lev)); RC(relax(lev, nsweeps)); CU(cudaStreamSynchronize(S.st)); return 0; }
+int mgb_residual(int lev, double* res) {
+  RC(check_level(lev)); RC(residual(lev));
+  double s = 0; RC(global_sum(lev, S.sums, &s)); *res = std::sqrt(s); return 0;
+}
+int mgb_fine2coarse(int lev) { RC(check_level(lev)); if (lev >= S.nlevs()) return fail("no coarser level"); RC(fine2coarse(lev, false)); CU(cudaStreamSynchronize(S.st)); return 0; }
+int mgb_coarse2fine(int lev) { RC(check_level(lev)); if (lev >= S.nlevs()) return fail("no coarser level"); RC(coarse2fine(lev, false)); CU(cudaStreamSynchronize(S.st)); return 0; }
+int mgb_fcycle(void) { RC(check_level(1)); RC(fcycle()); CU(cudaStreamSynchronize(S.st)); return 0; }
+int mgb_vcycle(int lev1) { RC(check_level(lev1)); RC(vcycle(lev1)); CU(cudaStreamSynchronize(S.st)); return 0; }
+int mgb_fill_halo(int lev, const char* name) {
+  RC(check_level(lev)); FieldRef f; RC(field_ref(lev, name, f));
+  if (f.is_cA) return fail("cA halo is only exchanged with bmask (not built)");
+  const LevelDims& d = S.L[lev - 1].d; const std::string n = name;
+  if (n == "zr") RC(fill_halo(lev, f.ptr, d.nz, 2)); else if (n == "zw") RC(fill_halo(lev, f.ptr, d.nz + 1, 2));
+  else if (n == "dx" || n == "dy" || n == "zeta" || n == "h") RC(fill_halo(lev, f.ptr, 1, 1));
+  else if (n == "cw" || n == "dzw") RC(fill_halo(lev, f.ptr, d.nz + 1, 1));
+  else RC(fill_halo(lev, f.ptr, d.nz, 1));
+  CU(cudaStreamSynchronize(S.st)); return 0;
+}
+
+long long mgb_field_size(int lev, const char* name) {
+  if (check_level(lev) != 0) return -1;
+  FieldRef f; if (field_ref(lev, name, f) != 0) return -1;
+  return (long long)f.n;
+}
+int mgb_get_field(int lev, const char* name, double* out) {
+  RC(check_level(lev)); FieldRef f; RC(field_ref(lev, name, f));
+  if (f.is_cA) {
+    double* tmp = nullptr; CU(cudaMalloc((void**)&tmp, f.n * sizeof(double)));
+    launch_soa_to_aos8(S.st, S.L[lev - 1].planes_dev, tmp, f.n / 8);
+    cudaError_t e = cudaMemcpyAsync(out, tmp, f.n * sizeof(double), cudaMemcpyDeviceToHost, S.st);
+    cudaStreamSynchronize(S.st); cudaFree(tmp);
+    if (e != cudaSuccess) return fail(cudaGetErrorString(e));
+    return 0;
+  }
+  CU(cudaMemcpyAsync(out, f.ptr, f.n * sizeof(double), cudaMemcpyDeviceToHost, S.st));
+  CU(cudaStreamSynchronize(S.st)); return 0;
+}
+int mgb_set_field(int lev, const char* name, const double* in) {
+  RC(check_level(lev)); FieldRef f; RC(field_ref(lev, name, f));
+  if (f.is_cA) {
+    Level& g = S.L[lev - 1];
+    double* tmp = nullptr; CU(cudaMalloc((void**)&tmp, f.n * sizeof(double)));
+    cudaError_t e = cudaMemcpyAsync(tmp, in, f.n * sizeof(double), cudaMemcpyHostToDevice, S.st);
+    launch_aos8_to_soa(S.st, tmp, g.planes_dev, f.n / 8);
+    cudaStreamSynchronize(S.st); cudaFree(tmp);
+    if (e != cudaSuccess) return fail(cudaGetErrorString(e));
+    launch_refresh_derived(S.st, matrix_view(g, lev));     // bet, g, c5b, c8b follow cA
+    CU(cudaStreamSynchronize(S.st));
+    return 0;
+  }
+  CU(cudaMemcpyAsync(f.ptr, in, f.n * sizeof(double), cudaMemcpyHostToDevice, S.st));
+  CU(cudaStreamSynchronize(S.st)); return 0;
+}
+
+long long mgb_launch_count(void) { return g_launches; }
+void mgb_reset_launch_count(void) { g_launches = 0; }
+
+int mgb_profile_level1(int reps, double* out4) {
+  if (!S.have_matrices) return fail("mgb_matrices has not been called");
+  if (S.nlevs() < 2) return fail("need at least two levels");
+  Level& g = S.L[0]; Level& c = S.L[1];
+  cudaEvent_t a, b; CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
+  float ms = 0;
+  const bool rank1 = (S.P.cmatrix == "real") && g.bottom_diag;
+  // relax: one colour = snapshot + A + B + C + halo
+  for (int pass = 0; pass < 2; ++pass) {
+    const int n = pass == 0 ? 2 : reps;
+    CU(cudaEventRecord(a, S.st));
+    for (int r = 0; r < n; ++r) {
+      ColourSet cs{1, 1, 0, 1 + (r & 1), 0, rank1 ? 1 : 0};
+      if (rank1) launch_snapshot_x1(S.st, g.v);
+      launch_relax_A(S.st, g.v, cs);
+      if (rank1) { launch_relax_B(S.st, g.v, cs); launch_relax_C(S.st, g.v, cs); }
+      RC(fill_halo(1, g.v.p, g.d.nz, 1));
+    }
+    CU(cudaEventRecord(b, S.st)); CU(cudaEventSynchronize(b)); CU(cudaEventElapsedTime(&ms, a, b));
+    out4[0] = ms / n;
+  }
+  for (int pass = 0; pass < 2; ++pass) {
+    const int n = pass == 0 ? 2 : reps;
+    CU(cudaEventRecord(a, S.st));
+    for (int r = 0; r < n; ++r) RC(residual(1));
+    CU(cudaEventRecord(b, S.st)); CU(cudaEventSynchronize(b)); CU(cudaEventElapsedTime(&ms, a, b));
+    out4[1] = ms / n;
+  }
+  if (!c.d.gather) {
+    for (int pass = 0; pass < 2; ++pass) {
+      const int n = pass == 0 ? 2 : reps;
+      CU(cudaEventRecord(a, S.st));
+      for (int r = 0; r < n; ++r) { launch_restrict8(S.st, g.v.r, g.d.nz, g.d.ny, g.d.nx, c.v.b, c.d.nz, c.d.ny, c.d.nx); RC(fill_halo(2, c.v.b, c.d.nz, 1)); launch_fill(S.st, c.v.p, 0.0, c.n3()); }
+      CU(cudaEventRecord(b, S.st)); CU(cudaEventSynchronize(b)); CU(cudaEventElapsedTime(&ms, a, b));
+      out4[2] = ms / n;
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+      const int n = pass == 0 ? 2 : reps;
+      CU(cudaEventRecord(a, S.st));
+      for (int r = 0; r < n; ++r) RC(coarse2fine(1, true));
+      CU(cudaEventRecord(b, S.st)); CU(cudaEventSynchronize(b)); CU(cudaEventElapsedTime(&ms, a, b));
+      out4[3] = ms / n;
+    }
+  } else { out4[2] = out4[3] = 0.0; }
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  return 0;
+}
+
+}  // extern "C"

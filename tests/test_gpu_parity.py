@@ -1,0 +1,183 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libmgb.so) against the CPU oracle.
+
+Compiled with -fmad=false, the kernels evaluate every expression in the oracle's (= the reference's)
+operation order, so matrix construction, rhs, residual, restriction and prolongation are compared BIT-EXACT;
+the red-black smoother is compared bit-exact against the oracle's rank-1 formulation (relax_order=1) and within
+round-off against the oracle in the reference's sequential sweep order (relax_order=0).
+"""
+import numpy as np
+import pytest
+
+from common import history_close, make_oracle, make_product, neumann_halo, random_interior, relerr, velocities
+
+pytestmark = pytest.mark.gpu
+
+CASES = [("seamount", 32, 32, 32), ("rndtopo", 16, 32, 16), ("cuc", 32, 16, 8)]
+
+
+@pytest.mark.parametrize("kind,nx,ny,nz", CASES)
+def test_define_matrices_bitexact(nh, kind, nx, ny, nz):
+    o = make_oracle(kind, nx, ny, nz)
+    make_product(nh, kind, nx, ny, nz)
+    assert nh.nlevs() == o.nlevs
+    for lev in range(1, o.nlevs + 1):
+        for name in ("dx", "dy", "zeta", "h", "zr", "zw", "cw", "cA"):
+            a, b = nh.get_field(name, lev), o.get(name, lev)
+            assert a.shape == b.shape
+            assert np.array_equal(a, b), (kind, lev, name, relerr(a, b))
+    for name in ("dzw", "zxdy", "zydx"):
+        assert np.array_equal(nh.get_field(name, 1), o.get(name, 1)), name
+
+
+@pytest.mark.parametrize("kind,nx,ny,nz", CASES)
+def test_compute_rhs_bitexact(nh, kind, nx, ny, nz):
+    o = make_oracle(kind, nx, ny, nz, uvw="random")
+    make_product(nh, kind, nx, ny, nz)
+    u, v, w = velocities("random", nx, ny, nz)
+    o.compute_rhs()
+    nh.compute_rhs(None, u, v, w)
+    a, b = nh.get_field("b", 1), o.get("b", 1)
+    assert np.array_equal(a[1:-1, 1:-1], b[1:-1, 1:-1]), relerr(a[1:-1, 1:-1], b[1:-1, 1:-1])
+
+
+@pytest.mark.parametrize("kind,nx,ny,nz", CASES)
+def test_residual_and_norm(nh, kind, nx, ny, nz):
+    o = make_oracle(kind, nx, ny, nz)
+    make_product(nh, kind, nx, ny, nz)
+    for lev in range(1, o.nlevs + 1):
+        shp = o.get("p", lev).shape
+        p = neumann_halo(random_interior(shp, 10 + lev)); b = random_interior(shp, 20 + lev)
+        o.set("p", p, lev); o.set("b", b, lev); nh.set_field("p", p, lev); nh.set_field("b", b, lev)
+        ro, rg = o.residual(lev), nh.compute_residual(lev)
+        assert np.array_equal(nh.get_field("r", lev), o.get("r", lev)), (lev, relerr(nh.get_field("r", lev), o.get("r", lev)))
+        assert abs(rg - ro) <= 1e-13 * ro, (lev, rg, ro)
+
+
+@pytest.mark.parametrize("kind,nx,ny,nz", CASES)
+@pytest.mark.parametrize("method", ["RB", "FC"])
+def test_relax(nh, kind, nx, ny, nz, method):
+    o1 = make_oracle(kind, nx, ny, nz, relax_method=method, relax_order=1)   # rank-1 formulation (what the GPU does)
+    o0 = make_oracle(kind, nx, ny, nz, relax_method=method, relax_order=0)   # reference sweep order
+    make_product(nh, kind, nx, ny, nz, relax_method=method)
+    for lev in range(1, o1.nlevs + 1):
+        shp = o1.get("p", lev).shape
+        p = neumann_halo(random_interior(shp, 30 + lev)); b = random_interior(shp, 40 + lev)
+        for o in (o0, o1):
+            o.set("p", p, lev); o.set("b", b, lev); o.relax(lev, 2)
+        nh.set_field("p", p, lev); nh.set_field("b", b, lev); nh.relax(lev, 2)
+        g = nh.get_field("p", lev)
+        assert np.array_equal(g, o1.get("p", lev)), (kind, method, lev, relerr(g, o1.get("p", lev)))
+        assert relerr(g, o0.get("p", lev)) < 1e-12, (kind, method, lev, relerr(g, o0.get("p", lev)))
+
+
+def test_relax_simple_matrix(nh):
+    o = make_oracle("seamount", 16, 16, 16, cmatrix="simple")
+    make_product(nh, "seamount", 16, 16, 16, cmatrix="simple")
+    shp = o.get("p", 1).shape
+    p = neumann_halo(random_interior(shp, 1)); b = random_interior(shp, 2)
+    o.set("p", p); o.set("b", b); o.relax(1, 3)
+    nh.set_field("p", p); nh.set_field("b", b); nh.relax(1, 3)
+    assert np.array_equal(nh.get_field("p"), o.get("p"))
+    assert abs(nh.compute_residual(1) - o.residual(1)) <= 1e-13 * o.residual(1)
+
+
+@pytest.mark.parametrize("kind,nx,ny,nz", CASES)
+@pytest.mark.parametrize("interp", ["linear", "nearest"])
+def test_intergrid_bitexact(nh, kind, nx, ny, nz, interp):
+    o = make_oracle(kind, nx, ny, nz, interp_type=interp)
+    make_product(nh, kind, nx, ny, nz, interp_type=interp)
+    for lev in range(1, o.nlevs):
+        shp = o.get("r", lev).shape
+        r = random_interior(shp, 50 + lev)
+        o.set("r", r, lev); nh.set_field("r", r, lev)
+        o.fine2coarse(lev); nh.fine2coarse(lev)
+        assert np.array_equal(nh.get_field("b", lev + 1), o.get("b", lev + 1)), ("restrict", lev)
+        assert not nh.get_field("p", lev + 1).any()
+        shc = o.get("p", lev + 1).shape
+        pc = neumann_halo(random_interior(shc, 60 + lev)); pf = neumann_halo(random_interior(shp, 70 + lev))
+        o.set("p", pc, lev + 1); o.set("p", pf, lev); nh.set_field("p", pc, lev + 1); nh.set_field("p", pf, lev)
+        o.coarse2fine(lev); nh.coarse2fine(lev)
+        assert np.array_equal(nh.get_field("r", lev), o.get("r", lev)), ("prolong r", lev)
+        assert np.array_equal(nh.get_field("p", lev), o.get("p", lev)), ("prolong p", lev)
+
+
+def test_intergrid_identities(nh):
+    """Restriction of a constant = 8x, prolongation of a constant = 1 (interior) and 1/2 at the top level."""
+    make_product(nh, "seamount", 16, 16, 16)
+    r = np.zeros(nh.get_field("r", 1).shape); r[1:-1, 1:-1] = 1.0
+    nh.set_field("r", r, 1); nh.fine2coarse(1)
+    assert np.array_equal(nh.get_field("b", 2)[1:-1, 1:-1], np.full((8, 8, 8), 8.0))
+    pc = np.ones(nh.get_field("p", 2).shape); nh.set_field("p", pc, 2)
+    nh.set_field("p", np.zeros(nh.get_field("p", 1).shape), 1); nh.coarse2fine(1)
+    pf = nh.get_field("p", 1)
+    assert np.array_equal(pf[1:-1, 1:-1, :-1], np.ones((16, 16, 15)))
+    assert np.array_equal(pf[1:-1, 1:-1, -1], np.full((16, 16), 0.5))
+
+
+@pytest.mark.parametrize("kind,nx,ny,nz", [("seamount", 32, 32, 32), ("rndtopo", 32, 32, 16)])
+def test_solve_history(nh, kind, nx, ny, nz):
+    prm = dict(solver_prec=1e-10, solver_maxiter=20)
+    o1 = make_oracle(kind, nx, ny, nz, relax_order=1, **prm); o1.compute_rhs(); o1.solve_p()
+    o0 = make_oracle(kind, nx, ny, nz, relax_order=0, **prm); o0.compute_rhs(); o0.solve_p()
+    make_product(nh, kind, nx, ny, nz, **prm)
+    nh.compute_rhs(None, *velocities("wminus1", nx, ny, nz)); nh.solve_p()
+    hg, _ = nh.history(); h1, _ = o1.history(); h0, _ = o0.history()
+    history_close(hg, h1, rtol=1e-12, floor=1e-16)        # same formulation: only the norm's summation order differs
+    history_close(hg, h0)                                  # reference sweep order: 1e-10 relative + round-off floor
+    assert relerr(nh.get_field("p"), o1.get("p")) < 1e-12
+    assert relerr(nh.get_field("p"), o0.get("p")) < 1e-9   # north-star bar on the final pressure
+
+
+def test_seamount64_history_matches_survey_numbers(nh):
+    """C1: seamount 64^3, src/nh_namelist parameters; first cycles vs BASELINE.md section 3 (independent restatement)."""
+    make_product(nh, "seamount", 64, 64, 64, solver_prec=1e-12, solver_maxiter=50)
+    nh.compute_rhs(None, *velocities("wminus1", 64, 64, 64)); nh.solve_p()
+    hg, _ = nh.history()
+    ref = [1.0, 7.2958980741680756e-04, 3.1837738515430506e-06, 4.2003277907156717e-08, 8.5429640221199814e-10]
+    for a, b in zip(hg, ref):
+        assert abs(a - b) <= 1e-6 * b, (hg, ref)
+    assert hg[-1] <= 1e-12 and len(hg) == 7
+
+
+def test_nhydro_solve_end_to_end(nh):
+    nx, ny, nz = 32, 32, 16
+    prm = dict(solver_prec=1e-10, solver_maxiter=20)
+    o = make_oracle("seamount", nx, ny, nz, uvw="random", relax_order=1, **prm)
+    o.nhydro_solve()
+    make_product(nh, "seamount", nx, ny, nz, **prm)
+    u, v, w = velocities("random", nx, ny, nz)
+    nh.nhydro_solve(nx, ny, nz, None, u, v, w)
+    uo, vo, wo = o.get_uvw(0)
+    assert relerr(u, uo) < 1e-10 and relerr(v, vo) < 1e-10 and relerr(w, wo) < 1e-10
+    history_close(nh.history()[0], o.history()[0], rtol=1e-12, floor=1e-16)
+    # and the corrected field is (nearly) non-divergent: reference's own check (nhydro.f90:105)
+    b0 = o.get("b", 1)
+    nh.nhydro_check_nondivergence(nx, ny, nz, None, u, v, w)
+    o.set_uvw(0, uo, vo, wo); o.compute_rhs()
+    assert np.array_equal(nh.get_field("b")[1:-1, 1:-1], o.get("b")[1:-1, 1:-1]) or relerr(nh.get_field("b")[1:-1, 1:-1], o.get("b")[1:-1, 1:-1]) < 1e-6
+
+
+def test_fused_prolong_equals_reference_sequence(nh, monkeypatch):
+    """The F-cycle uses p += P p_c fused; MGB_EXACT_STATE=1 runs the reference's r=P p_c; halo; p+=r. Same p."""
+    res = []
+    for exact in ("0", "1"):
+        monkeypatch.setenv("MGB_EXACT_STATE", exact)
+        make_product(nh, "seamount", 32, 32, 16, solver_prec=1e-9)
+        nh.compute_rhs(None, *velocities("wminus1", 32, 32, 16)); nh.solve_p()
+        res.append((nh.history()[0], nh.get_field("p")))
+        nh.nhydro_clean()
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+
+
+def test_errors_are_loud(nh):
+    with pytest.raises(nh.MgbError):
+        nh.solve_p()                                   # before init
+    nh.set_params(relax_method="GS")
+    nh.nhydro_init(16, 16, 16)
+    from common import geometry
+    (dx, dy, zeta, h), vert = geometry("seamount", 16, 16, 16)
+    nh.nhydro_matrices(dx, dy, zeta, h, None, **vert)
+    with pytest.raises(nh.MgbError):
+        nh.relax(1, 1)                                 # GS is not built: must say so, not fall back
+    with pytest.raises(nh.MgbError):
+        nh.get_field("nope")
