@@ -31,6 +31,9 @@ void launch_snapshot_x1(cudaStream_t st, const LevelView& L);
 void launch_relax_A(cudaStream_t st, const LevelView& L, const ColourSet& cs);
 void launch_relax_B(cudaStream_t st, const LevelView& L, const ColourSet& cs);
 void launch_relax_C(cudaStream_t st, const LevelView& L, const ColourSet& cs);
+// whole relax(lev, nsweeps) of a small, neighbour-free level in one single-CTA launch (red-black only)
+bool relax_small_supported(const LevelView& L);
+void launch_relax_small(cudaStream_t st, const LevelView& L, int nsweeps, int rank1);
 
 // ---- residual + norm (src/mg_relax.f90:337-515) ----------------------------------------------------------
 // r = b - A p on the interior; partial sums of r^2 per block into `partials`, then reduced in fixed order to *sum_out.
@@ -69,6 +72,7 @@ struct MatrixView {
 };
 void launch_define_matrix(cudaStream_t st, const MatrixView& M);
 void launch_refresh_derived(cudaStream_t st, const MatrixView& M);   // c5b, c8b, bet, g, g1 from the cA planes
+void launch_rho(cudaStream_t st, const MatrixView& M, double* out_dev);   // contraction factor of the bottom recurrence
 // max(|c5b|,|c8b|) > 0 ?  result (0/1) written to *flag_dev
 void launch_any_nonzero2(cudaStream_t st, const double* a, const double* b, size_t n, int* flag_dev);
 

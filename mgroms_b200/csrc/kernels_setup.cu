@@ -215,6 +215,26 @@ void launch_refresh_derived(cudaStream_t st, const MatrixView& M) {
   k_thomas_setup<<<blocks_for((size_t)M.ny * M.nx, 128), 128, 0, st>>>(M); ++g_launches;
 }
 
+// contraction factor of the bottom recurrence: rho = max over interior columns of |g1 c5b| + |g1 c8b|
+__global__ void __launch_bounds__(1024) k_rho(MatrixView M, double* out) {
+  __shared__ double s_red[32];
+  const int ny = M.ny, nx = M.nx, ny2 = ny + 2;
+  double v = 0.0;
+  for (int e = threadIdx.x; e < ny * nx; e += blockDim.x) {
+    const int j = 1 + e % ny, i = 1 + e / ny; const size_t c = (size_t)j + (size_t)ny2 * i;
+    v = fmax(v, fabs(M.g1[c] * M.c5b[c]) + fabs(M.g1[c] * M.c8b[c]));
+  }
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    v = s_red[threadIdx.x];
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+    if (threadIdx.x == 0) *out = v;
+  }
+}
+void launch_rho(cudaStream_t st, const MatrixView& M, double* out_dev) { k_rho<<<1, 1024, 0, st>>>(M, out_dev); ++g_launches; }
+
 __global__ void k_any_nonzero2(const double* __restrict__ a, const double* __restrict__ b, size_t n, int* flag) {
   size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
   int any = 0;

@@ -324,40 +324,86 @@ void launch_relax_A(cudaStream_t st, const LevelView& L, const ColourSet& cs) {
 
 // Kernel B: the sequential part of the red-black bottom coupling, on the 2-D k=1 plane only.
 // For i ascending: s(j,i) = -(c5b(j,i) x1(j+1,i-1) + c8b(j,i) x1(j-1,i-1)) ; x1(j,i) = q1(j,i) + s(j,i) g1(j,i)
-// One CTA; the previous column of x1 lives in shared memory (two ping-pong rows).
+// One CTA marches over i.  x1(:,i-1) lives in shared memory (two ping-pong rows); the five operand rows of the
+// coming steps (c5b, c8b, q1, g1 and the old x1 for the halo entries) are streamed into a D-deep shared-memory
+// ring with cp.async (LDGSTS) so that no global-memory latency sits on the dependency chain.
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+template <int D, bool ONE_WARP>
 __global__ void __launch_bounds__(1024) k_relax_B(LevelView L, ColourSet cs) {
-  extern __shared__ double sm[];
-  const int ny = L.ny, nx = L.nx, ny2 = ny + 2;
-  double* row0 = sm;            // x1(:, i-1)
-  double* row1 = sm + ny2;      // x1(:, i)
-  for (int j = threadIdx.x; j < ny2; j += blockDim.x) row0[j] = L.x1[j];          // column i = 0 (halo, old values)
-  __syncthreads();
-  double* prev = row0; double* cur = row1;
-  for (int i = 1; i <= nx; ++i) {
-    const int js = colour_jstart(cs, i);
-    const size_t col = (size_t)ny2 * i;
-    // entries of column i that are not updated by this colour keep their old value (other colour, halo rows)
-    for (int j = threadIdx.x; j < ny2; j += blockDim.x) {
-      const bool mine = (j >= js) && (j <= ny) && (((j - js) & 1) == 0);
-      double v;
-      if (mine) {
-        const double sv = -(L.c5b[col + j] * prev[j + 1] + L.c8b[col + j] * prev[j - 1]);
-        v = L.q1[col + j] + sv * L.g1[col + j];
-        L.s[col + j] = sv;
-        L.x1[col + j] = v;
-      } else {
-        v = L.x1[col + j];
+  extern __shared__ __align__(16) double sm[];
+  const int ny = L.ny, nx = L.nx, ny2 = ny + 2, nyc = (ny + 1) / 2;
+  // this CTA commits s(:, c0..c1); it starts W columns earlier from the OLD x1 (contraction: error ~ rho^W)
+  const int c0 = 1 + blockIdx.x * L.rb_chunk, c1 = min(nx, c0 + L.rb_chunk - 1), i0 = max(1, c0 - L.rb_W);
+  const int nsteps = c1 - i0 + 1;
+  double* row0 = sm;                 // x1(:, i-1)
+  double* row1 = sm + ny2;           // x1(:, i)
+  double* ring = sm + 2 * ny2;       // [D][5][ny2]
+  const double* planes[5] = {L.c5b, L.c8b, L.q1, L.g1, L.x1};
+  const int chunks_per_row = ny2 / 2;              // 16-byte chunks (ny2 is even)
+  auto issue = [&](int step) {                     // step = 0.. ; column i0 + step
+    if (step < nsteps) {
+      double* slot = ring + (size_t)(step % D) * 5 * ny2;
+      const size_t col = (size_t)ny2 * (i0 + step);
+      for (int c = threadIdx.x; c < 5 * chunks_per_row; c += blockDim.x) {
+        const int a = c / chunks_per_row, q = c % chunks_per_row;
+        cp_async16(slot + a * ny2 + 2 * q, planes[a] + col + 2 * q);
       }
-      cur[j] = v;
     }
-    __syncthreads();
+    cp_async_commit();
+  };
+  auto barrier = [&]() { if (ONE_WARP) __syncwarp(); else __syncthreads(); };
+  for (int j = threadIdx.x; j < ny2; j += blockDim.x) row0[j] = L.x1[(size_t)ny2 * (i0 - 1) + j];
+  for (int d = 0; d <= D - 2; ++d) issue(d);
+  double* prev = row0; double* cur = row1;
+  for (int st = 0; st < nsteps; ++st) {
+    const int i = i0 + st;
+    cp_async_wait<D - 2>();
+    barrier();
+    issue(st + D - 1);
+    const double* slot = ring + (size_t)(st % D) * 5 * ny2;
+    const double *r5 = slot, *r8 = slot + ny2, *rq = slot + 2 * ny2, *rg = slot + 3 * ny2, *rx = slot + 4 * ny2;
+    const int js = 1 + ((i + cs.rb) & 1);
+    const size_t col = (size_t)ny2 * i;
+    for (int jc = threadIdx.x; jc < nyc; jc += blockDim.x) {
+      const int j = js + 2 * jc;
+      if (j <= ny) {
+        const double sv = -(r5[j] * prev[j + 1] + r8[j] * prev[j - 1]);
+        cur[j] = rq[j] + sv * rg[j];
+        if (i >= c0) L.s[col + j] = sv;
+      }
+    }
+    if (threadIdx.x == 0) { cur[0] = rx[0]; cur[ny + 1] = rx[ny + 1]; }
     double* t = prev; prev = cur; cur = t;
   }
+  cp_async_wait<0>();
 }
 void launch_relax_B(cudaStream_t st, const LevelView& L, const ColourSet& cs) {
-  int threads = 32; while (threads < L.ny + 2 && threads < 1024) threads *= 2;
-  size_t smem = (size_t)2 * (L.ny + 2) * sizeof(double);
-  k_relax_B<<<1, threads, smem, st>>>(L, cs); ++g_launches;
+  const int ny2 = L.ny + 2, nyc = (L.ny + 1) / 2;
+  int threads = 32; while (threads < nyc && threads < 1024) threads *= 2;
+  // ring depth by shared-memory budget (<= ~200 KB): rows are ny2 doubles, 5 rows per step
+  int D = 8;
+  while (D > 2 && (size_t)(2 + 5 * D) * ny2 * sizeof(double) > 200 * 1024) D /= 2;
+  const size_t smem = (size_t)(2 + 5 * D) * ny2 * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_relax_B<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(k_relax_B<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(k_relax_B<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(k_relax_B<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    attr_set = true;
+  }
+  const int nchunks = (L.nx + L.rb_chunk - 1) / L.rb_chunk;
+  if (threads == 32 && D == 8) k_relax_B<8, true><<<nchunks, 32, smem, st>>>(L, cs);
+  else if (D == 8) k_relax_B<8, false><<<nchunks, threads, smem, st>>>(L, cs);
+  else if (D == 4) k_relax_B<4, false><<<nchunks, threads, smem, st>>>(L, cs);
+  else k_relax_B<2, false><<<nchunks, threads, smem, st>>>(L, cs);
+  ++g_launches;
 }
 
 // Kernel C: p(:,j,i) += s(j,i) * g(:,j,i) on the columns of the colour
@@ -380,6 +426,155 @@ void launch_relax_C(cudaStream_t st, const LevelView& L, const ColourSet& cs) {
   const int nvi = (L.nx - cs.istart) / cs.istep + 1;
   dim3 grid(blocks_for((size_t)nyc * L.nz, 256), nvi);
   k_relax_C<<<grid, 256, 0, st>>>(L, cs, nyc); ++g_launches;
+}
+
+// Fused relaxation of a SMALL level: all `nsweeps` red-black sweeps (both colours, bottom-coupling recurrence,
+// correction and the Neumann halo of p) in ONE launch of ONE CTA.  Coarse levels are launch/latency bound: this
+// replaces 10*nsweeps launches by one.  Only valid when the level has no lateral neighbour rank (single GPU, or
+// a level gathered onto one rank).  Same arithmetic, operation by operation, as kernels A/B/C + halo.
+//   shared memory: five 2-D planes (x1, q1, c5b, c8b, g1) of (ny+2)*(nx+2) doubles + per-warp x1 rows
+template <int NZ>
+__global__ void __launch_bounds__(1024) k_relax_small(LevelView L, int nsweeps, int rank1) {
+  extern __shared__ __align__(16) double sm[];
+  const int nx = L.nx, ny = L.ny, ny2 = ny + 2, nyc = ny / 2;
+  const int n2 = ny2 * (nx + 2);
+  double *x1 = sm, *q1 = sm + n2, *c5b = sm + 2 * n2, *c8b = sm + 3 * n2, *g1 = sm + 4 * n2, *rows = sm + 5 * n2;   // rows: [8 warps][2][ny2]
+  const int sj = NZ; const int si = NZ * ny2;
+  double* __restrict__ p = L.p;
+  const double* __restrict__ b = L.b;
+  const double* __restrict__ c2 = L.cA[1]; const double* __restrict__ c3 = L.cA[2]; const double* __restrict__ c4 = L.cA[3];
+  const double* __restrict__ c5 = L.cA[4]; const double* __restrict__ c6 = L.cA[5]; const double* __restrict__ c7 = L.cA[6];
+  const double* __restrict__ c8 = L.cA[7]; const double* __restrict__ bet = L.bet; const double* __restrict__ g = L.g;
+  if (rank1) for (int e = threadIdx.x; e < n2; e += blockDim.x) { c5b[e] = L.c5b[e]; c8b[e] = L.c8b[e]; g1[e] = L.g1[e]; }
+  __syncthreads();
+  for (int it = 0; it < nsweeps; ++it) for (int rb = 1; rb <= 2; ++rb) {
+    if (rank1) { for (int e = threadIdx.x; e < n2; e += blockDim.x) x1[e] = p[(size_t)e * NZ]; __syncthreads(); }
+    // ---- A: thread per column
+    for (int c = threadIdx.x; c < nx * nyc; c += blockDim.x) {
+      const int i = 1 + c / nyc, jc = c % nyc;
+      const int j = 1 + ((i + rb) & 1) + 2 * jc;
+      const int idx0 = NZ * (j + ny2 * i);
+      double x[NZ];
+#pragma unroll
+      for (int k = 0; k < NZ; ++k) {
+        const int idx = idx0 + k;
+        double acc = b[idx];
+        if (k < NZ - 1) acc = acc - c3[idx] * p[idx - sj + 1];
+        if (k > 0)      acc = acc - c3[idx + sj - 1] * p[idx + sj - 1];
+        acc = acc - c4[idx] * p[idx - sj];
+        acc = acc - c4[idx + sj] * p[idx + sj];
+        if (k > 0)      acc = acc - c5[idx] * p[idx - sj - 1];
+        if (k < NZ - 1) acc = acc - c5[idx + sj + 1] * p[idx + sj + 1];
+        if (k < NZ - 1) acc = acc - c6[idx] * p[idx - si + 1];
+        if (k > 0)      acc = acc - c6[idx + si - 1] * p[idx + si - 1];
+        acc = acc - c7[idx] * p[idx - si];
+        acc = acc - c7[idx + si] * p[idx + si];
+        if (k > 0)      acc = acc - c8[idx] * p[idx - si - 1];
+        if (k < NZ - 1) acc = acc - c8[idx + si + 1] * p[idx + si + 1];
+        if (k == 0 && rank1) {
+          const int c2d = j + ny2 * i;
+          acc = acc - c5b[c2d - 1 + ny2] * x1[c2d - 1 + ny2];
+          acc = acc - c8b[c2d + 1 + ny2] * x1[c2d + 1 + ny2];
+        }
+        x[k] = acc;
+      }
+      double xm = x[0] * bet[idx0];
+      x[0] = xm;
+#pragma unroll
+      for (int k = 1; k < NZ; ++k) { xm = (x[k] - c2[idx0 + k] * xm) * bet[idx0 + k]; x[k] = xm; }
+#pragma unroll
+      for (int k = NZ - 2; k >= 0; --k) { xm = x[k] - (c2[idx0 + k + 1] * bet[idx0 + k]) * xm; x[k] = xm; }
+#pragma unroll
+      for (int k = 0; k < NZ; ++k) p[idx0 + k] = x[k];
+      if (rank1) q1[j + ny2 * i] = xm;
+    }
+    __syncthreads();
+    if (rank1) {
+      // ---- B: chunked bottom recurrence, one warp per chunk (same chunks and warm-up as kernel B)
+      {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+        const int wpar = nwarps < 8 ? nwarps : 8;
+        const int nchunks = (nx + L.rb_chunk - 1) / L.rb_chunk;
+        if (warp < wpar) {
+          double* prev = rows + warp * 2 * ny2; double* cur = prev + ny2;
+          for (int c = warp; c < nchunks; c += wpar) {
+            const int c0 = 1 + c * L.rb_chunk, c1 = min(nx, c0 + L.rb_chunk - 1), i0 = max(1, c0 - L.rb_W);
+            for (int j = lane; j < ny2; j += 32) prev[j] = x1[j + ny2 * (i0 - 1)];
+            __syncwarp();
+            for (int i = i0; i <= c1; ++i) {
+              const int js = 1 + ((i + rb) & 1);
+              for (int jc = lane; jc < nyc; jc += 32) {
+                const int j = js + 2 * jc, c2d = j + ny2 * i;
+                const double sv = -(c5b[c2d] * prev[j + 1] + c8b[c2d] * prev[j - 1]);
+                cur[j] = q1[c2d] + sv * g1[c2d];
+                if (i >= c0) L.s[c2d] = sv;
+              }
+              if (lane == 0) { cur[0] = x1[ny2 * i]; cur[ny + 1] = x1[ny + 1 + ny2 * i]; }
+              __syncwarp();
+              double* t = prev; prev = cur; cur = t;
+            }
+          }
+        }
+      }
+      __syncthreads();
+      // ---- C: p += s g on the colour's columns
+      for (int c = threadIdx.x; c < nx * nyc; c += blockDim.x) {
+        const int i = 1 + c / nyc, jc = c % nyc;
+        const int j = 1 + ((i + rb) & 1) + 2 * jc;
+        const int idx0 = NZ * (j + ny2 * i);
+        const double sv = L.s[j + ny2 * i];
+#pragma unroll
+        for (int k = 0; k < NZ; ++k) p[idx0 + k] = p[idx0 + k] + sv * g[idx0 + k];
+      }
+      __syncthreads();
+    }
+    // ---- halo of p: homogeneous Neumann on all four sides + corners
+    for (int e = threadIdx.x; e < 2 * ny * NZ; e += blockDim.x) {
+      const int side = e / (ny * NZ), rem = e % (ny * NZ);
+      if (side == 0) p[NZ * (1 + ny2 * 0) + rem] = p[NZ * (1 + ny2 * 1) + rem];
+      else p[NZ * (1 + ny2 * (nx + 1)) + rem] = p[NZ * (1 + ny2 * nx) + rem];
+    }
+    for (int e = threadIdx.x; e < 2 * nx * NZ; e += blockDim.x) {
+      const int side = e / (nx * NZ), rem = e % (nx * NZ);
+      const int i = 1 + rem / NZ, k = rem % NZ;
+      if (side == 0) p[k + NZ * (0 + ny2 * i)] = p[k + NZ * (1 + ny2 * i)];
+      else p[k + NZ * (ny + 1 + ny2 * i)] = p[k + NZ * (ny + ny2 * i)];
+    }
+    for (int e = threadIdx.x; e < 4 * NZ; e += blockDim.x) {
+      const int cc = e / NZ, k = e % NZ;
+      if (cc == 0) p[k + NZ * (0 + ny2 * 0)] = p[k + NZ * (1 + ny2 * 1)];
+      if (cc == 1) p[k + NZ * (0 + ny2 * (nx + 1))] = p[k + NZ * (1 + ny2 * nx)];
+      if (cc == 2) p[k + NZ * (ny + 1 + ny2 * (nx + 1))] = p[k + NZ * (ny + ny2 * nx)];
+      if (cc == 3) p[k + NZ * (ny + 1 + ny2 * 0)] = p[k + NZ * (ny + ny2 * 1)];
+    }
+    __syncthreads();
+  }
+}
+bool relax_small_supported(const LevelView& L) {
+  const size_t n2 = (size_t)(L.ny + 2) * (L.nx + 2);
+  const bool nz_ok = (L.nz == 2 || L.nz == 4 || L.nz == 8 || L.nz == 16);
+  return nz_ok && (L.ny % 2 == 0) && (n2 * 5 + (size_t)16 * (L.ny + 2)) * sizeof(double) <= 220 * 1024;
+}
+void launch_relax_small(cudaStream_t st, const LevelView& L, int nsweeps, int rank1) {
+  const size_t n2 = (size_t)(L.ny + 2) * (L.nx + 2);
+  const size_t smem = (n2 * 5 + (size_t)16 * (L.ny + 2)) * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_relax_small<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    cudaFuncSetAttribute(k_relax_small<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    cudaFuncSetAttribute(k_relax_small<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    cudaFuncSetAttribute(k_relax_small<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    attr_set = true;
+  }
+  int threads = 64; const int ncol = L.nx * (L.ny / 2);
+  while (threads < ncol && threads < 1024) threads *= 2;
+  switch (L.nz) {
+    case 2: k_relax_small<2><<<1, threads, smem, st>>>(L, nsweeps, rank1); break;
+    case 4: k_relax_small<4><<<1, threads, smem, st>>>(L, nsweeps, rank1); break;
+    case 8: k_relax_small<8><<<1, threads, smem, st>>>(L, nsweeps, rank1); break;
+    default: k_relax_small<16><<<1, threads, smem, st>>>(L, nsweeps, rank1); break;
+  }
+  ++g_launches;
 }
 
 // =====================================================================================================

@@ -43,7 +43,11 @@ struct LevelView {
   double *g;          // g = T^-1 e1 (rank-1 correction vector of the red-black bottom coupling)
   double *c5b, *c8b;  // 2-D copies of cA(5,1,:,:), cA(8,1,:,:) (bottom diagonal couplings)
   double *g1, *q1, *x1, *s;   // 2-D work planes of the rank-1 correction
+  int rb_chunk, rb_W;         // the bottom recurrence runs in independent chunks of rb_chunk columns warmed up over rb_W columns
 };
+// warm-up length of the chunked bottom recurrence: smallest w with rho^w <= 1e-20 (rho = contraction factor)
+inline int rb_warmup(double rho) { int w = 0; double acc = 1.0; while (acc > 1e-20 && w < 64) { acc *= rho; ++w; } return w; }
+constexpr int RB_CHUNK = 8, RB_WMAX = 24;
 
 struct Halo1Flags { int south, east, north, west, sw, se, ne, nw; };  // 1 = neighbour exists
 

@@ -72,6 +72,7 @@ struct Level {
   double *partials = nullptr; int npartials = 0;
   Halo1Flags hf{};
   bool bottom_diag = true;
+  double rho = 0.0;
   size_t n3() const { return (size_t)d.nz * (d.ny + 2) * (d.nx + 2); }
   size_t n2() const { return (size_t)(d.ny + 2) * (d.nx + 2); }
 };
@@ -93,6 +94,7 @@ struct Solver {
   std::vector<double> hist_res, hist_conv;
   double last_ms = 0; int last_iters = 0;
   bool fused_prolong = true;
+  bool use_small = true;             // fused single-CTA relaxation on small neighbour-free levels
   int nlevs() const { return (int)L.size(); }
 };
 static Solver S;
@@ -206,6 +208,11 @@ static int relax(int lev, int nsweeps) {
   const std::string& m = S.P.relax_method;
   const bool real_matrix = (S.P.cmatrix == "real");
   if (m == "Red-Black" || m == "RB") {
+    bool lonely = true; for (int q = 0; q < 8; ++q) lonely &= g.d.neighb[q] < 0;
+    if (S.use_small && lonely && relax_small_supported(g.v)) {
+      launch_relax_small(S.st, g.v, nsweeps, (real_matrix && g.bottom_diag) ? 1 : 0);
+      return 0;
+    }
     for (int it = 0; it < nsweeps; ++it)
       for (int rb = 1; rb <= 2; ++rb) {
         ColourSet cs{1, 1, 0, rb, 0, 0};
@@ -389,6 +396,13 @@ static int define_matrices() {
     CU(cudaMemcpyAsync(&flag, S.flag_dev, sizeof(int), cudaMemcpyDeviceToHost, S.st));
     CU(cudaStreamSynchronize(S.st));
     g.bottom_diag = flag != 0;
+    launch_rho(S.st, matrix_view(g, lev), S.sums + 3);
+    double rho = 0.0;
+    CU(cudaMemcpyAsync(&rho, S.sums + 3, sizeof(double), cudaMemcpyDeviceToHost, S.st));
+    CU(cudaStreamSynchronize(S.st));
+    g.rho = rho;
+    g.v.rb_W = rb_warmup(rho);
+    g.v.rb_chunk = (g.v.rb_W > RB_WMAX) ? g.d.nx : RB_CHUNK;
   }
   CU(cudaStreamSynchronize(S.st));
   S.have_matrices = true;
@@ -512,7 +526,7 @@ static int init(int nx, int ny, int nz, int npx, int npy, int rank, const char* 
     Level& g = S.L[q]; g.d = plan[q]; g.hf = flags_of(g.d);
     const LevelDims& d = g.d; const int lev = (int)q + 1;
     const size_t n3 = g.n3(), n2 = g.n2();
-    g.v.nx = d.nx; g.v.ny = d.ny; g.v.nz = d.nz;
+    g.v.nx = d.nx; g.v.ny = d.ny; g.v.nz = d.nz; g.v.rb_chunk = d.nx; g.v.rb_W = 0;
     RC(dalloc(&g.v.p, n3)); RC(dalloc(&g.v.b, n3)); RC(dalloc(&g.v.r, n3));
     for (int c = 0; c < 8; ++c) RC(dalloc(&g.v.cA[c], n3));
     RC(dalloc(&g.v.bet, n3)); RC(dalloc(&g.v.g, n3));
@@ -546,6 +560,8 @@ static int init(int nx, int ny, int nz, int npx, int npy, int rank, const char* 
     void* fp = nullptr; CU(cudaMalloc(&fp, sizeof(int))); S.allocs.push_back(fp); S.flag_dev = (int*)fp; }
   const char* ex = std::getenv("MGB_EXACT_STATE");
   S.fused_prolong = !(ex && ex[0] == '1');
+  const char* ns = std::getenv("MGB_NO_SMALL_KERNEL");
+  S.use_small = !(ns && ns[0] == '1');
   CU(cudaStreamSynchronize(S.st));
   S.inited = true;
   g_plan = plan;
@@ -731,7 +747,11 @@ int mgb_set_field(int lev, const char* name, const double* in) {
     cudaStreamSynchronize(S.st); cudaFree(tmp);
     if (e != cudaSuccess) return fail(cudaGetErrorString(e));
     launch_refresh_derived(S.st, matrix_view(g, lev));     // bet, g, c5b, c8b follow cA
+    launch_rho(S.st, matrix_view(g, lev), S.sums + 3);
+    double rho = 0.0;
+    CU(cudaMemcpyAsync(&rho, S.sums + 3, sizeof(double), cudaMemcpyDeviceToHost, S.st));
     CU(cudaStreamSynchronize(S.st));
+    g.rho = rho; g.v.rb_W = rb_warmup(rho); g.v.rb_chunk = (g.v.rb_W > RB_WMAX) ? g.d.nx : RB_CHUNK;
     return 0;
   }
   CU(cudaMemcpyAsync(f.ptr, in, f.n * sizeof(double), cudaMemcpyHostToDevice, S.st));

@@ -762,29 +762,55 @@ static void rb_colour_reference(const Grid& g, int rb, bool real_matrix) {
 //   A: q = T^-1 rhs0, rhs0 has OLD values in the two (i+1) bottom-diagonal terms and omits the (i-1) ones
 //   B: for i ascending: s = -(cA5(1,j,i) x1(j+1,i-1) + cA8(1,j,i) x1(j-1,i-1)); x1(j,i) = q1 + s g1
 //   C: p = q + s g, g = T^-1 e1
+// B is a contraction (rho = max |g1 cA5| + |g1 cA8| is ~1e-2), so it is evaluated in independent chunks of
+// RB_CHUNK columns, each warmed up over W columns starting from the OLD x1: the start-up error decays like
+// rho^W <= 1e-20, i.e. far below one ulp.  W > RB_WMAX falls back to one sequential chunk.
+static const int RB_CHUNK = 8, RB_WMAX = 24;
+static int rb_warmup(double rho) { int w = 0; double acc = 1.0; while (acc > 1e-20 && w < 64) { acc *= rho; ++w; } return w; }
 static void rb_colour_rank1(const Grid& g, int rb, bool real_matrix) {
   const int nx = g.nx, ny = g.ny, nz = g.nz; const A3& p = g.p; const A4& cA = g.cA;
-  std::vector<double> x1((size_t)(ny + 2) * (nx + 2)), s((size_t)(ny + 2) * (nx + 2), 0.0), ws(5 * nz);
-  auto X1 = [&](int j, int i) -> double& { return x1[(size_t)j + (size_t)(ny + 2) * i]; };
-  auto S = [&](int j, int i) -> double& { return s[(size_t)j + (size_t)(ny + 2) * i]; };
-  for (int i = 0; i <= nx + 1; ++i) for (int j = 0; j <= ny + 1; ++j) X1(j, i) = p(1, j, i);     // snapshot
+  const size_t n2 = (size_t)(ny + 2) * (nx + 2);
+  std::vector<double> x1(n2), q1(n2, 0.0), s(n2, 0.0), g1(n2, 0.0), gfull((size_t)nz * n2, 0.0), ws(5 * nz);
+  auto I2 = [&](int j, int i) { return (size_t)j + (size_t)(ny + 2) * i; };
+  for (int i = 0; i <= nx + 1; ++i) for (int j = 0; j <= ny + 1; ++j) x1[I2(j, i)] = p(1, j, i);     // snapshot
   double *rhs = ws.data(), *d = rhs + nz, *ud = d + nz, *gam = ud + nz;
-  for (int i = 1; i <= nx; ++i) for (int j = 1 + (i + rb) % 2; j <= ny; j += 2) {                 // A
+  for (int i = 1; i <= nx; ++i) for (int j = 1 + (i + rb) % 2; j <= ny; j += 2) {                     // A
     column_rhs(g, i, j, false, rhs, d, ud);
-    if (real_matrix) rhs[0] = rhs[0] - cA(5, 1, j - 1, i + 1) * X1(j - 1, i + 1) - cA(8, 1, j + 1, i + 1) * X1(j + 1, i + 1);
+    if (real_matrix) rhs[0] = rhs[0] - cA(5, 1, j - 1, i + 1) * x1[I2(j - 1, i + 1)] - cA(8, 1, j + 1, i + 1) * x1[I2(j + 1, i + 1)];
     tridiag(nz, d, ud, rhs, &p(1, j, i), gam);
+    q1[I2(j, i)] = p(1, j, i);
   }
   if (!real_matrix) return;
-  std::vector<double> e1(nz), gg(nz);
-  for (int i = 1; i <= nx; ++i) for (int j = 1 + (i + rb) % 2; j <= ny; j += 2) {                 // B (+C inline)
+  // g = T^-1 e1 for every interior column, rho over ALL interior columns (both colours), as at matrix-build time
+  std::vector<double> e1(nz);
+  double rho = 0.0; bool any = false;
+  for (int i = 1; i <= nx; ++i) for (int j = 1; j <= ny; ++j) {
     for (int k = 1; k <= nz; ++k) { d[k - 1] = cA(1, k, j, i); if (k < nz) ud[k - 1] = cA(2, k + 1, j, i); e1[k - 1] = 0.0; }
     e1[0] = 1.0;
-    tridiag(nz, d, ud, e1.data(), gg.data(), gam);
-    double sv = -(cA(5, 1, j, i) * X1(j + 1, i - 1) + cA(8, 1, j, i) * X1(j - 1, i - 1));
-    S(j, i) = sv;
-    X1(j, i) = p(1, j, i) + sv * gg[0];
-    for (int k = 1; k <= nz; ++k) p(k, j, i) = p(k, j, i) + sv * gg[k - 1];                        // C
+    tridiag(nz, d, ud, e1.data(), &gfull[(size_t)nz * I2(j, i)], gam);
+    g1[I2(j, i)] = gfull[(size_t)nz * I2(j, i)];
+    rho = std::max(rho, std::fabs(g1[I2(j, i)] * cA(5, 1, j, i)) + std::fabs(g1[I2(j, i)] * cA(8, 1, j, i)));
   }
+  for (int i = 1; i <= nx + 1 && !any; ++i) for (int j = 0; j <= ny + 1; ++j) if (cA(5, 1, j, i) != 0.0 || cA(8, 1, j, i) != 0.0) { any = true; break; }
+  if (!any) return;                                            // flat bottom: no same-colour coupling
+  const int W = rb_warmup(rho);
+  const int chunk = (W > RB_WMAX) ? nx : RB_CHUNK;
+  std::vector<double> prev(ny + 2), cur(ny + 2);
+  for (int c0 = 1; c0 <= nx; c0 += chunk) {                                                           // B
+    const int c1 = std::min(nx, c0 + chunk - 1), i0 = std::max(1, c0 - W);
+    for (int j = 0; j <= ny + 1; ++j) prev[j] = x1[I2(j, i0 - 1)];
+    for (int i = i0; i <= c1; ++i) {
+      for (int j = 1 + (i + rb) % 2; j <= ny; j += 2) {
+        const double sv = -(cA(5, 1, j, i) * prev[j + 1] + cA(8, 1, j, i) * prev[j - 1]);
+        cur[j] = q1[I2(j, i)] + sv * g1[I2(j, i)];
+        if (i >= c0) s[I2(j, i)] = sv;
+      }
+      cur[0] = x1[I2(0, i)]; cur[ny + 1] = x1[I2(ny + 1, i)];
+      std::swap(prev, cur);
+    }
+  }
+  for (int i = 1; i <= nx; ++i) for (int j = 1 + (i + rb) % 2; j <= ny; j += 2)                       // C
+    for (int k = 1; k <= nz; ++k) p(k, j, i) = p(k, j, i) + s[I2(j, i)] * gfull[(size_t)nz * I2(j, i) + k - 1];
 }
 
 static void relax(World& W, int lev, int nsweeps) {
