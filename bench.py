@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native MGROMS pressure solver.
+
+Metric (BASELINE.json): ms per multigrid solve of the non-hydrostatic pressure Poisson problem to relative
+residual 1e-10 (p = 0 start, the reference's solve_p loop, src/mg_solvers.f90:17-101), plus the achieved HBM
+bandwidth of the dominant kernel (one colour of the red-black line relaxation) against the measured roofline.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+N = 1 : workload = BASELINE config[1], seamount 512x512x64 on one B200.
+N > 1 : weak scaling, one 512x512x64 sub-domain per GPU (npx x npy = 2x1, 2x2, 4x2), launched with torchrun.
+A "step" is one full solve (all F-cycles until res/bnorm <= 1e-10) with the right-hand side resident in HBM.
+`e2e` is the same solve through the reference-facing call nhydro_solve(nx,ny,nz,rmask,u,v,w) with HOST arrays
+(pinned), i.e. H2D of u,v,w + compute_rhs + solve + correct_uvw + D2H inside the timed region.
+--impl reference times the CPU oracle (restated reference path, one thread per emulated MPI rank).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BLOCK = (512, 512, 64)            # per-GPU sub-domain (nx, ny, nz) = BASELINE config[1]
+KIND = "seamount"
+TOL = 1e-10
+PROC_GRID = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (4, 2)}     # src/mg_grids.f90:593-594 rank <-> (pi,pj)
+BYTES_PER_POINT = dict(relax_colour=68, residual=88, restrict=10, prolong=17)
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True); self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_grid(cores: int):
+    """Largest power-of-two process grid (npx >= npy) with npx*npy <= cores: the reference runs one MPI rank per core."""
+    n = 1
+    while n * 2 <= cores:
+        n *= 2
+    npx = 1
+    while npx * npx < n:
+        npx *= 2
+    return npx, n // npx
+
+
+def run_oracle(global_dims, reps: int, cores: int):
+    """Times the CPU oracle's solve_p on the global grid `global_dims`, one thread per emulated rank."""
+    from oracle.pyoracle import make_case, lib
+    nxg, nyg, nz = global_dims
+    npx, npy = cpu_grid(cores)
+    lib().mgo_set_num_threads(npx * npy)
+    o = make_case(KIND, nxg // npx, nyg // npy, nz, npx, npy, bench_dx=True, solver_prec=TOL, solver_maxiter=50)
+    o.compute_rhs()
+    times = []
+    for _ in range(reps):
+        o.solve_p()
+        times.append(o.solve_seconds * 1e3)
+    hist = o.history()[0]
+    return dict(ms=float(np.mean(times)), iters=len(hist) - 1, npx=npx, npy=npy, final=float(hist[-1]))
+
+
+def reference_arm(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    nx, ny, nz = BLOCK
+    reps = max(1, args.steps)
+    for _ in range(max(0, min(args.warmup, 1))):
+        run_oracle((nx, ny, nz), 1, cores)
+    r = run_oracle((nx, ny, nz), reps, cores)
+    scale = args.gpus     # weak scaling: N GPUs solve N sub-domains; the CPU does the same work N times over
+    value = r["ms"] * scale
+    sample = (f"CPU oracle (C++ restatement of the Fortran/MPI path; no Fortran compiler or MPI in this image), "
+              f"{r['npx']}x{r['npy']} emulated ranks = threads, full {nx}x{ny}x{nz} seamount solve to 1e-10 "
+              f"({r['iters']} F-cycles), {reps} timed solve(s)" + (f", time scaled x{scale} for the {scale}-sub-domain weak-scaled job" if scale > 1 else ""))
+    out = {
+        "impl": "reference", "metric": "ms per MG solve to rel. residual 1e-10", "value": value, "unit": "ms",
+        "n_gpus": args.gpus, "steps": reps, "warmup": min(args.warmup, 1), "ms_per_step": value, "higher_is_better": False,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "ms", "cores": r["npx"] * r["npy"], "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def config_dict(n):
+    npx, npy = PROC_GRID[n]
+    nx, ny, nz = BLOCK
+    return {"workload": f"seamount {nx * npx}x{ny * npy}x{nz} (BASELINE config[1] block {nx}x{ny}x{nz} per GPU, dx=dy=156.25 m), "
+                        f"u=v=0,w=-1, F-cycles to res/bnorm<=1e-10, namelist src/nh_namelist (ns_pre=3, ns_post=2, ns_coarsest=40, RB, linear)",
+            "parallelism": f"{npx}x{npy} sub-domains, one per GPU", "l2": "inputs larger than L2 (level-1 coefficients 1.1 GB per GPU)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus not in PROC_GRID:
+        raise SystemExit("--gpus must be 1, 2, 4 or 8")
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} needs WORLD_SIZE={args.gpus} (launch with torch.distributed.run); got {world}")
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from mgroms_b200 import nhydro as nh, testcases as tc
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    npx, npy = PROC_GRID[args.gpus]
+    nx, ny, nz = BLOCK
+
+    nh.reset_params()
+    prm = dict(solver_prec=TOL, solver_maxiter=50)
+    if world > 1:
+        prm["nsmall"] = 64      # gather the coarse levels onto one rank each (mg_gather) so they run latency-free of halo exchanges
+    nh.set_params(**prm)
+    nh.nhydro_init(nx, ny, nz, npx, npy, rank, device=local)
+    if world > 1:
+        box = [nh.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        nh.comm_init(box[0])
+    (dx, dy, zeta, h), vert = tc.bench_geometry(KIND, nx, ny, nz, npx, npy, rank)
+    nh.nhydro_matrices(dx, dy, zeta, h, None, vert["hc"], vert["theta_b"], vert["theta_s"])
+
+    def pinned(shape):
+        return torch.empty(shape, dtype=torch.float64, pin_memory=True).numpy()
+    u0, v0, w0 = tc.uvw_wminus1(nx, ny, nz)
+    u, v, w = pinned(u0.shape), pinned(v0.shape), pinned(w0.shape)
+    u[...] = u0; v[...] = v0; w[...] = w0
+    nh.compute_rhs(None, u, v, w)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident solve: W warm-up + K timed steps
+    for _ in range(args.warmup):
+        nh.solve_p()
+    barrier()
+    sampler = ClockSampler(local); sampler.start()
+    nh.reset_launch_count()
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    for _ in range(args.steps):
+        nh.solve_p()
+        dev_ms += nh.last_solve_ms()       # CUDA events on the solver's stream around the solve_p loop
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    launches = nh.launch_count()
+    clocks = sampler.stop()
+    iters = nh.last_solve_iters()
+    hist = nh.history()[0]
+    tt = torch.tensor([dev_ms / args.steps, wall_ms / args.steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_per_step, wall_per_step = float(tt[0]), float(tt[1])
+
+    # ---- end to end through nhydro_solve with host buffers
+    e2e_ms = 0.0
+    n_e2e = max(2, min(args.steps, 5))
+    for it in range(n_e2e + 1):
+        u[...] = u0; v[...] = v0; w[...] = w0
+        barrier()
+        t1 = time.perf_counter()
+        nh.nhydro_solve(nx, ny, nz, None, u, v, w)
+        torch.cuda.synchronize()
+        if it > 0:
+            e2e_ms += (time.perf_counter() - t1) * 1e3
+    te = torch.tensor([e2e_ms / n_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    h2d = (u.nbytes + v.nbytes + w.nbytes) * world
+    d2h = h2d
+
+    # ---- roofline of the dominant kernel class (one colour of the relaxation at level 1), CUDA events on the solver stream
+    prof = nh.profile_level1(10)
+    peak, peak_kind = measured_peaks()
+    npts = nx * ny * nz
+    ach = BYTES_PER_POINT["relax_colour"] * npts / (prof["relax_colour_ms"] * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get("relax_colour_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                "peak_source": peak_kind, "kernel": "relax colour half-sweep, level 1 (k_snapshot_x1 + k_relax_A + k_relax_B + k_relax_C + k_halo1_phys)",
+                "algorithmic_bytes_per_launch": BYTES_PER_POINT["relax_colour"] * npts,
+                "others_GBps": {k: BYTES_PER_POINT[k] * npts / (prof[k + "_ms"] * 1e-3) / 1e9 for k in ("residual", "restrict", "prolong")}}
+
+    if rank == 0:
+        out = {
+            "metric": "ms per MG solve to rel. residual 1e-10", "value": ms_per_step, "unit": "ms", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args.gpus),
+            "fcycles_per_solve": iters, "final_rel_residual": float(hist[-1]), "wall_ms_per_step": wall_per_step,
+            "e2e": {"value": float(te[0]), "unit": "ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+        }
+        if args.gpus == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            r = run_oracle((nx, ny, nz), 2, cores)
+            out["cpu_baseline"] = {"value": r["ms"], "unit": "ms", "cores": r["npx"] * r["npy"], "kind": "port",
+                                   "sample": f"CPU oracle (restated reference path), {r['npx']}x{r['npy']} emulated MPI ranks = threads, the same full "
+                                             f"{nx}x{ny}x{nz} solve to 1e-10 ({r['iters']} F-cycles), mean of 2 solves"}
+        print(json.dumps(out), flush=True)
+    nh.nhydro_clean()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
