@@ -6,6 +6,7 @@
 namespace mgb {
 
 extern long long g_launches;   // number of kernel launches issued by this library
+void kernels_init();           // one-time function attributes (dynamic shared memory limits)
 
 // ---- halo (single-GPU part: physical edges; src/mg_mpi_exchange.f90) ---------------------------------
 // nh = 1 array a(nzl, 0:ny+1, 0:nx+1): homogeneous-Neumann mirror on edges without neighbour, physical corners.

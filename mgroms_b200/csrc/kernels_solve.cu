@@ -214,7 +214,7 @@ __device__ __forceinline__ int colour_jstart(const ColourSet& cs, int i) { retur
 //   dynamic smem: 3 arrays [TC][nz+1] : rhs/x, bet, ud
 // Thomas recurrences (src/mg_relax.f90:308-334) with the pivots' reciprocals `bet` precomputed at matrix time:
 //   x(1) = rhs(1)*bet(1) ; x(k) = (rhs(k) - ud(k-1)*x(k-1))*bet(k) ; back: x(k) -= (ud(k)*bet(k))*x(k+1)
-__global__ void __launch_bounds__(256) k_relax_A(LevelView L, ColourSet cs, int TI, int TJ, int ntj) {
+__global__ void __launch_bounds__(256, 2) k_relax_A(LevelView L, ColourSet cs, int TI, int TJ, int ntj) {
   extern __shared__ double sm[];
   const int nz = L.nz, ny2 = L.ny + 2, pitch = nz + 1;
   const int TC = TI * TJ;
@@ -240,34 +240,51 @@ __global__ void __launch_bounds__(256) k_relax_A(LevelView L, ColourSet cs, int 
     const int j = colour_jstart(cs, i) + 2 * (tile_j * TJ + cj);
     if (j > L.ny) continue;
     const size_t idx = IDX3(k, j, i, nz, ny2);
-    double acc = b[idx];
-    if (k < nz - 1) acc = acc - c3[idx] * p[idx - sj + 1];
-    if (k > 0)      acc = acc - c3[idx + sj - 1] * p[idx + sj - 1];
-    acc = acc - c4[idx] * p[idx - sj];
-    acc = acc - c4[idx + sj] * p[idx + sj];
-    if (k > 0)      acc = acc - c5[idx] * p[idx - sj - 1];
-    if (k < nz - 1) acc = acc - c5[idx + sj + 1] * p[idx + sj + 1];
-    if (k < nz - 1) acc = acc - c6[idx] * p[idx - si + 1];
-    if (k > 0)      acc = acc - c6[idx + si - 1] * p[idx + si - 1];
-    acc = acc - c7[idx] * p[idx - si];
-    acc = acc - c7[idx + si] * p[idx + si];
-    if (k > 0)      acc = acc - c8[idx] * p[idx - si - 1];
-    if (k < nz - 1) acc = acc - c8[idx + si + 1] * p[idx + si + 1];
+    // all operands are loaded up front and unconditionally (every address is inside the arrays: the k-1 / k+1
+    // neighbours of an end point fall into the adjacent column) so that ~27 loads per thread are in flight at
+    // once; the edge predicates only select which products enter the sum -- same terms, same order as before.
+    const double bb = b[idx], bt = bet[idx], udv = c2[idx + 1];
+    const double a3 = c3[idx],           q3 = p[idx - sj + 1];
+    const double a3n = c3[idx + sj - 1], q3n = p[idx + sj - 1];
+    const double a4 = c4[idx],           q4 = p[idx - sj];
+    const double a4n = c4[idx + sj],     q4n = p[idx + sj];
+    const double a5 = c5[idx],           q5 = p[idx - sj - 1];
+    const double a5n = c5[idx + sj + 1], q5n = p[idx + sj + 1];
+    const double a6 = c6[idx],           q6 = p[idx - si + 1];
+    const double a6n = c6[idx + si - 1], q6n = p[idx + si - 1];
+    const double a7 = c7[idx],           q7 = p[idx - si];
+    const double a7n = c7[idx + si],     q7n = p[idx + si];
+    const double a8 = c8[idx],           q8 = p[idx - si - 1];
+    const double a8n = c8[idx + si + 1], q8n = p[idx + si + 1];
+    const bool lo = (k > 0), hi = (k < nz - 1);
+    double acc = bb;
+    if (hi) acc = acc - a3 * q3;
+    if (lo) acc = acc - a3n * q3n;
+    acc = acc - a4 * q4;
+    acc = acc - a4n * q4n;
+    if (lo) acc = acc - a5 * q5;
+    if (hi) acc = acc - a5n * q5n;
+    if (hi) acc = acc - a6 * q6;
+    if (lo) acc = acc - a6n * q6n;
+    acc = acc - a7 * q7;
+    acc = acc - a7n * q7n;
+    if (lo) acc = acc - a8 * q8;
+    if (hi) acc = acc - a8n * q8n;
     if (k == 0) {
       if (cs.bottom_mode == 1) {          // rank-1 form: only the two not-yet-updated (i+1) neighbours, from the snapshot
         const size_t c2d = (size_t)j + (size_t)ny2 * i;
         acc = acc - L.c5b[c2d - 1 + ny2] * L.x1[c2d - 1 + ny2];
         acc = acc - L.c8b[c2d + 1 + ny2] * L.x1[c2d + 1 + ny2];
       } else if (cs.bottom_mode == 2) {   // all four bottom-diagonal terms from p (src/mg_relax.f90:271-276)
-        acc = acc - c5[idx] * p[idx + sj - si];
+        acc = acc - a5 * p[idx + sj - si];
         acc = acc - c5[idx - sj + si] * p[idx - sj + si];
-        acc = acc - c8[idx] * p[idx - sj - si];
+        acc = acc - a8 * p[idx - sj - si];
         acc = acc - c8[idx + sj + si] * p[idx + sj + si];
       }
     }
     s_rhs[c * pitch + k] = acc;
-    s_bet[c * pitch + k] = bet[idx];
-    s_ud[c * pitch + k] = (k < nz - 1) ? c2[idx + 1] : 0.0;
+    s_bet[c * pitch + k] = bt;
+    s_ud[c * pitch + k] = hi ? udv : 0.0;
   }
   __syncthreads();
 
@@ -305,8 +322,8 @@ __global__ void __launch_bounds__(256) k_relax_A(LevelView L, ColourSet cs, int 
 static void relax_tiling(const LevelView& L, const ColourSet& cs, int& TI, int& TJ, int& nti, int& ntj, size_t& smem) {
   const int nyc = (L.ny + 1) / 2;                    // colour columns per visited i (upper bound)
   const int nvi = (L.nx - cs.istart) / cs.istep + 1; // visited i
-  int tc_max = 4096 / L.nz;                          // columns per CTA: aim at ~4096 points per tile
-  if (tc_max < 32) tc_max = 32;
+  int tc_max = 2048 / L.nz;                          // columns per CTA: aim at ~2048 points per tile (8 per thread)
+  if (tc_max < 16) tc_max = 16;
   if (tc_max > 1024) tc_max = 1024;
   while (tc_max > 1 && (size_t)tc_max * (L.nz + 1) * 3 * sizeof(double) > 56 * 1024) tc_max /= 2;
   TJ = nyc < tc_max ? nyc : tc_max;
@@ -317,8 +334,6 @@ static void relax_tiling(const LevelView& L, const ColourSet& cs, int& TI, int& 
 void launch_relax_A(cudaStream_t st, const LevelView& L, const ColourSet& cs) {
   int TI, TJ, nti, ntj; size_t smem;
   relax_tiling(L, cs, TI, TJ, nti, ntj, smem);
-  static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(k_relax_A, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
   k_relax_A<<<nti * ntj, 256, smem, st>>>(L, cs, TI, TJ, ntj); ++g_launches;
 }
 
@@ -350,10 +365,9 @@ __global__ void __launch_bounds__(1024) k_relax_B(LevelView L, ColourSet cs) {
     if (step < nsteps) {
       double* slot = ring + (size_t)(step % D) * 5 * ny2;
       const size_t col = (size_t)ny2 * (i0 + step);
-      for (int c = threadIdx.x; c < 5 * chunks_per_row; c += blockDim.x) {
-        const int a = c / chunks_per_row, q = c % chunks_per_row;
-        cp_async16(slot + a * ny2 + 2 * q, planes[a] + col + 2 * q);
-      }
+#pragma unroll
+      for (int a = 0; a < 5; ++a)
+        for (int q = threadIdx.x; q < chunks_per_row; q += blockDim.x) cp_async16(slot + a * ny2 + 2 * q, planes[a] + col + 2 * q);
     }
     cp_async_commit();
   };
@@ -390,14 +404,6 @@ void launch_relax_B(cudaStream_t st, const LevelView& L, const ColourSet& cs) {
   int D = 8;
   while (D > 2 && (size_t)(2 + 5 * D) * ny2 * sizeof(double) > 200 * 1024) D /= 2;
   const size_t smem = (size_t)(2 + 5 * D) * ny2 * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_relax_B<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    cudaFuncSetAttribute(k_relax_B<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    cudaFuncSetAttribute(k_relax_B<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    cudaFuncSetAttribute(k_relax_B<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    attr_set = true;
-  }
   const int nchunks = (L.nx + L.rb_chunk - 1) / L.rb_chunk;
   if (threads == 32 && D == 8) k_relax_B<8, true><<<nchunks, 32, smem, st>>>(L, cs);
   else if (D == 8) k_relax_B<8, false><<<nchunks, threads, smem, st>>>(L, cs);
@@ -550,22 +556,25 @@ __global__ void __launch_bounds__(1024) k_relax_small(LevelView L, int nsweeps, 
     __syncthreads();
   }
 }
+void kernels_init() {
+  cudaFuncSetAttribute(k_relax_A, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_relax_B<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  cudaFuncSetAttribute(k_relax_B<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  cudaFuncSetAttribute(k_relax_B<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  cudaFuncSetAttribute(k_relax_B<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  cudaFuncSetAttribute(k_relax_small<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+  cudaFuncSetAttribute(k_relax_small<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+  cudaFuncSetAttribute(k_relax_small<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+  cudaFuncSetAttribute(k_relax_small<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+}
 bool relax_small_supported(const LevelView& L) {
   const size_t n2 = (size_t)(L.ny + 2) * (L.nx + 2);
   const bool nz_ok = (L.nz == 2 || L.nz == 4 || L.nz == 8 || L.nz == 16);
-  return nz_ok && (L.ny % 2 == 0) && (n2 * 5 + (size_t)16 * (L.ny + 2)) * sizeof(double) <= 220 * 1024;
+  return nz_ok && (L.ny % 2 == 0) && n2 <= (size_t)34 * 34;
 }
 void launch_relax_small(cudaStream_t st, const LevelView& L, int nsweeps, int rank1) {
   const size_t n2 = (size_t)(L.ny + 2) * (L.nx + 2);
   const size_t smem = (n2 * 5 + (size_t)16 * (L.ny + 2)) * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_relax_small<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-    cudaFuncSetAttribute(k_relax_small<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-    cudaFuncSetAttribute(k_relax_small<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-    cudaFuncSetAttribute(k_relax_small<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-    attr_set = true;
-  }
   int threads = 64; const int ncol = L.nx * (L.ny / 2);
   while (threads < ncol && threads < 1024) threads *= 2;
   switch (L.nz) {
@@ -594,7 +603,7 @@ __device__ __forceinline__ double block_sum_256(double v, double* s_red) {
 }
 
 // one block handles a chunk of one i-slab: elements (k, j) flattened, j = 1..ny
-__global__ void __launch_bounds__(256) k_residual(LevelView L, int real_matrix, int chunks_per_i, double* __restrict__ partials) {
+__global__ void __launch_bounds__(256, 2) k_residual(LevelView L, int real_matrix, int chunks_per_i, double* __restrict__ partials) {
   __shared__ double s_red[8];
   const int nz = L.nz, ny = L.ny, ny2 = ny + 2;
   const int i = 1 + blockIdx.x / chunks_per_i, chunk = blockIdx.x % chunks_per_i;
@@ -611,26 +620,43 @@ __global__ void __launch_bounds__(256) k_residual(LevelView L, int real_matrix, 
   for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
     const int k = e % nz, j = 1 + e / nz;
     const size_t idx = IDX3(k, j, i, nz, ny2);
-    double acc = b[idx];
-    acc = acc - c1[idx] * p[idx];
-    if (k > 0)      acc = acc - c2[idx] * p[idx - 1];
-    if (k < nz - 1) acc = acc - c2[idx + 1] * p[idx + 1];
-    if (k < nz - 1) acc = acc - c3[idx] * p[idx - sj + 1];
-    if (k > 0)      acc = acc - c3[idx + sj - 1] * p[idx + sj - 1];
-    acc = acc - c4[idx] * p[idx - sj];
-    acc = acc - c4[idx + sj] * p[idx + sj];
-    if (k > 0)      acc = acc - c5[idx] * p[idx - sj - 1];
-    if (k < nz - 1) acc = acc - c5[idx + sj + 1] * p[idx + sj + 1];
-    if (k < nz - 1) acc = acc - c6[idx] * p[idx - si + 1];
-    if (k > 0)      acc = acc - c6[idx + si - 1] * p[idx + si - 1];
-    acc = acc - c7[idx] * p[idx - si];
-    acc = acc - c7[idx + si] * p[idx + si];
-    if (k > 0)      acc = acc - c8[idx] * p[idx - si - 1];
-    if (k < nz - 1) acc = acc - c8[idx + si + 1] * p[idx + si + 1];
+    const double bb = b[idx];
+    const double a1 = c1[idx],           q1v = p[idx];
+    const double a2 = c2[idx],           q2 = p[idx - 1];
+    const double a2n = c2[idx + 1],      q2n = p[idx + 1];
+    const double a3 = c3[idx],           q3 = p[idx - sj + 1];
+    const double a3n = c3[idx + sj - 1], q3n = p[idx + sj - 1];
+    const double a4 = c4[idx],           q4 = p[idx - sj];
+    const double a4n = c4[idx + sj],     q4n = p[idx + sj];
+    const double a5 = c5[idx],           q5 = p[idx - sj - 1];
+    const double a5n = c5[idx + sj + 1], q5n = p[idx + sj + 1];
+    const double a6 = c6[idx],           q6 = p[idx - si + 1];
+    const double a6n = c6[idx + si - 1], q6n = p[idx + si - 1];
+    const double a7 = c7[idx],           q7 = p[idx - si];
+    const double a7n = c7[idx + si],     q7n = p[idx + si];
+    const double a8 = c8[idx],           q8 = p[idx - si - 1];
+    const double a8n = c8[idx + si + 1], q8n = p[idx + si + 1];
+    const bool lo = (k > 0), hi = (k < nz - 1);
+    double acc = bb;
+    acc = acc - a1 * q1v;
+    if (lo) acc = acc - a2 * q2;
+    if (hi) acc = acc - a2n * q2n;
+    if (hi) acc = acc - a3 * q3;
+    if (lo) acc = acc - a3n * q3n;
+    acc = acc - a4 * q4;
+    acc = acc - a4n * q4n;
+    if (lo) acc = acc - a5 * q5;
+    if (hi) acc = acc - a5n * q5n;
+    if (hi) acc = acc - a6 * q6;
+    if (lo) acc = acc - a6n * q6n;
+    acc = acc - a7 * q7;
+    acc = acc - a7n * q7n;
+    if (lo) acc = acc - a8 * q8;
+    if (hi) acc = acc - a8n * q8n;
     if (k == 0 && real_matrix) {
-      acc = acc - c5[idx] * p[idx + sj - si];
+      acc = acc - a5 * p[idx + sj - si];
       acc = acc - c5[idx - sj + si] * p[idx - sj + si];
-      acc = acc - c8[idx] * p[idx - sj - si];
+      acc = acc - a8 * p[idx - sj - si];
       acc = acc - c8[idx + sj + si] * p[idx + sj + si];
     }
     r[idx] = acc;

@@ -95,6 +95,9 @@ struct Solver {
   double last_ms = 0; int last_iters = 0;
   bool fused_prolong = true;
   bool use_small = true;             // fused single-CTA relaxation on small neighbour-free levels
+  bool use_graph = true;             // replay one captured F-cycle (+ residual) per outer iteration
+  cudaGraphExec_t cycle_graph = nullptr;
+  long long cycle_graph_nodes = 0;
   int nlevs() const { return (int)L.size(); }
 };
 static Solver S;
@@ -306,6 +309,26 @@ static int fcycle() {
   return 0;
 }
 
+// One outer iteration (Fcycle + compute_residual(1)) captured into a CUDA graph: the launch sequence is fixed once
+// the matrices are defined, so each iteration becomes one graph launch instead of thousands of API calls.
+static int build_cycle_graph() {
+  cudaGraph_t graph = nullptr;
+  const long long before = g_launches;
+  CU(cudaStreamBeginCapture(S.st, cudaStreamCaptureModeThreadLocal));
+  int rc = fcycle();
+  if (rc == 0) rc = residual(1);
+  cudaError_t e = cudaStreamEndCapture(S.st, &graph);
+  S.cycle_graph_nodes = g_launches - before;
+  g_launches = before;
+  if (rc != 0) { if (graph) cudaGraphDestroy(graph); return rc; }
+  if (e != cudaSuccess) return fail(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+  e = cudaGraphInstantiate(&S.cycle_graph, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) return fail(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+  return 0;
+}
+static void drop_cycle_graph() { if (S.cycle_graph) { cudaGraphExecDestroy(S.cycle_graph); S.cycle_graph = nullptr; } }
+
 static int solve_p() {
   if (!S.have_matrices) return fail("mgb_matrices has not been called");
   Level& g = S.L[0];
@@ -322,8 +345,15 @@ static int solve_p() {
   double res0 = rnorm / bnorm;
   S.hist_res.assign(1, res0); S.hist_conv.assign(1, 0.0);
   while (nite < maxite && res0 > tol) {
-    RC(fcycle());
-    RC(residual(1)); RC(global_sum(1, S.sums, &rsum));
+    if (S.use_graph) {
+      if (!S.cycle_graph) RC(build_cycle_graph());
+      CU(cudaGraphLaunch(S.cycle_graph, S.st));
+      g_launches += S.cycle_graph_nodes;
+    } else {
+      RC(fcycle());
+      RC(residual(1));
+    }
+    RC(global_sum(1, S.sums, &rsum));
     rnorm = std::sqrt(rsum) / bnorm;
     const double conv = res0 / rnorm;
     res0 = rnorm;
@@ -367,7 +397,9 @@ static MatrixView matrix_view(Level& g, int lev) {
   return M;
 }
 
+static void drop_cycle_graph();
 static int define_matrices() {
+  drop_cycle_graph();
   for (int lev = 1; lev <= S.nlevs(); ++lev) {
     Level& g = S.L[lev - 1];
     if (lev > 1) {
@@ -493,6 +525,7 @@ static int correct_uvw_device() {
 // ------------------------------------------------------------------------------------------------------
 static int clean() {
   if (S.st) cudaStreamSynchronize(S.st);
+  drop_cycle_graph();
   for (void* p : S.allocs) cudaFree(p);
   S.allocs.clear();
   if (S.comm && g_nccl.CommDestroy) { g_nccl.CommDestroy(S.comm); }
@@ -562,6 +595,9 @@ static int init(int nx, int ny, int nz, int npx, int npy, int rank, const char* 
   S.fused_prolong = !(ex && ex[0] == '1');
   const char* ns = std::getenv("MGB_NO_SMALL_KERNEL");
   S.use_small = !(ns && ns[0] == '1');
+  const char* ng = std::getenv("MGB_NO_GRAPH");
+  S.use_graph = !(ng && ng[0] == '1');
+  kernels_init();
   CU(cudaStreamSynchronize(S.st));
   S.inited = true;
   g_plan = plan;
@@ -746,6 +782,7 @@ int mgb_set_field(int lev, const char* name, const double* in) {
     launch_aos8_to_soa(S.st, tmp, g.planes_dev, f.n / 8);
     cudaStreamSynchronize(S.st); cudaFree(tmp);
     if (e != cudaSuccess) return fail(cudaGetErrorString(e));
+    drop_cycle_graph();
     launch_refresh_derived(S.st, matrix_view(g, lev));     // bet, g, c5b, c8b follow cA
     launch_rho(S.st, matrix_view(g, lev), S.sums + 3);
     double rho = 0.0;
