@@ -36,6 +36,10 @@ int mgb_init(int nx, int ny, int nz, int npx, int npy, int rank, const char* nam
 int mgb_set_param(const char* key, const char* value);
 int mgb_reset_params(void);
 
+/* Host-only: parse `namelist_path` (NULL/"" = ./nh_namelist) like mgb_init would, apply the mgb_set_param overrides and
+ * write "key=value;..." for the 13 keys (+ file=0|1: whether a file was found) to out.  No device needed. */
+int mgb_namelist_probe(const char* namelist_path, char* out, int cap);
+
 /* Inter-GPU transport for npx*npy > 1 (replaces MPI_COMM_WORLD of src/mg_mpi_exchange.f90 and the
  * MPI_COMM_SPLIT sub-communicators of src/mg_grids.f90:717).  Rank 0 fills a 128-byte id with
  * mgb_comm_unique_id, the caller broadcasts it (any side channel), every rank calls mgb_comm_init. */

@@ -326,6 +326,7 @@ static void relax_tiling(const LevelView& L, const ColourSet& cs, int& TI, int& 
   if (tc_max < 16) tc_max = 16;
   if (tc_max > 1024) tc_max = 1024;
   while (tc_max > 1 && (size_t)tc_max * (L.nz + 1) * 3 * sizeof(double) > 56 * 1024) tc_max /= 2;
+  while (tc_max * L.nz > 256 && ((size_t)nyc * nvi + tc_max - 1) / tc_max < 296) tc_max /= 2;   // small level: more, smaller tiles
   TJ = nyc < tc_max ? nyc : tc_max;
   TI = tc_max / TJ; if (TI < 1) TI = 1; if (TI > nvi) TI = nvi;
   ntj = (nyc + TJ - 1) / TJ; nti = (nvi + TI - 1) / TI;
@@ -440,17 +441,24 @@ void launch_relax_C(cudaStream_t st, const LevelView& L, const ColourSet& cs) {
 // a level gathered onto one rank).  Same arithmetic, operation by operation, as kernels A/B/C + halo.
 //   shared memory: five 2-D planes (x1, q1, c5b, c8b, g1) of (ny+2)*(nx+2) doubles + per-warp x1 rows
 template <int NZ>
-__global__ void __launch_bounds__(1024) k_relax_small(LevelView L, int nsweeps, int rank1) {
+__global__ void __launch_bounds__(1024) k_relax_small(LevelView L, int nsweeps, int rank1, int all_smem) {
   extern __shared__ __align__(16) double sm[];
   const int nx = L.nx, ny = L.ny, ny2 = ny + 2, nyc = ny / 2;
   const int n2 = ny2 * (nx + 2);
   double *x1 = sm, *q1 = sm + n2, *c5b = sm + 2 * n2, *c8b = sm + 3 * n2, *g1 = sm + 4 * n2, *rows = sm + 5 * n2;   // rows: [8 warps][2][ny2]
   const int sj = NZ; const int si = NZ * ny2;
-  double* __restrict__ p = L.p;
-  const double* __restrict__ b = L.b;
-  const double* __restrict__ c2 = L.cA[1]; const double* __restrict__ c3 = L.cA[2]; const double* __restrict__ c4 = L.cA[3];
-  const double* __restrict__ c5 = L.cA[4]; const double* __restrict__ c6 = L.cA[5]; const double* __restrict__ c7 = L.cA[6];
-  const double* __restrict__ c8 = L.cA[7]; const double* __restrict__ bet = L.bet; const double* __restrict__ g = L.g;
+  // the 3-D operands stay in global memory (L2) or, when the whole level fits (all_smem), are staged in shared memory
+  double* p = L.p;
+  const double* b = L.b;
+  const double *c2 = L.cA[1], *c3 = L.cA[2], *c4 = L.cA[3], *c5 = L.cA[4], *c6 = L.cA[5], *c7 = L.cA[6], *c8 = L.cA[7], *bet = L.bet, *g = L.g;
+  const int n3 = NZ * n2;
+  if (all_smem) {
+    double* base = rows + 16 * ny2;
+    const double* src[11] = {L.p, L.b, L.cA[1], L.cA[2], L.cA[3], L.cA[4], L.cA[5], L.cA[6], L.cA[7], L.bet, L.g};
+    for (int a = 0; a < 11; ++a) for (int e = threadIdx.x; e < n3; e += blockDim.x) base[a * n3 + e] = src[a][e];
+    p = base; b = base + n3; c2 = base + 2 * n3; c3 = base + 3 * n3; c4 = base + 4 * n3; c5 = base + 5 * n3; c6 = base + 6 * n3;
+    c7 = base + 7 * n3; c8 = base + 8 * n3; bet = base + 9 * n3; g = base + 10 * n3;
+  }
   if (rank1) for (int e = threadIdx.x; e < n2; e += blockDim.x) { c5b[e] = L.c5b[e]; c8b[e] = L.c8b[e]; g1[e] = L.g1[e]; }
   __syncthreads();
   for (int it = 0; it < nsweeps; ++it) for (int rb = 1; rb <= 2; ++rb) {
@@ -555,6 +563,7 @@ __global__ void __launch_bounds__(1024) k_relax_small(LevelView L, int nsweeps, 
     }
     __syncthreads();
   }
+  if (all_smem) for (int e = threadIdx.x; e < n3; e += blockDim.x) L.p[e] = p[e];
 }
 void kernels_init() {
   cudaFuncSetAttribute(k_relax_A, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -574,14 +583,17 @@ bool relax_small_supported(const LevelView& L) {
 }
 void launch_relax_small(cudaStream_t st, const LevelView& L, int nsweeps, int rank1) {
   const size_t n2 = (size_t)(L.ny + 2) * (L.nx + 2);
-  const size_t smem = (n2 * 5 + (size_t)16 * (L.ny + 2)) * sizeof(double);
+  size_t smem = (n2 * 5 + (size_t)16 * (L.ny + 2)) * sizeof(double);
+  const size_t smem_all = smem + (size_t)11 * L.nz * n2 * sizeof(double);
+  const int all_smem = smem_all <= 226 * 1024 ? 1 : 0;
+  if (all_smem) smem = smem_all;
   int threads = 64; const int ncol = L.nx * (L.ny / 2);
   while (threads < ncol && threads < 1024) threads *= 2;
   switch (L.nz) {
-    case 2: k_relax_small<2><<<1, threads, smem, st>>>(L, nsweeps, rank1); break;
-    case 4: k_relax_small<4><<<1, threads, smem, st>>>(L, nsweeps, rank1); break;
-    case 8: k_relax_small<8><<<1, threads, smem, st>>>(L, nsweeps, rank1); break;
-    default: k_relax_small<16><<<1, threads, smem, st>>>(L, nsweeps, rank1); break;
+    case 2: k_relax_small<2><<<1, threads, smem, st>>>(L, nsweeps, rank1, all_smem); break;
+    case 4: k_relax_small<4><<<1, threads, smem, st>>>(L, nsweeps, rank1, all_smem); break;
+    case 8: k_relax_small<8><<<1, threads, smem, st>>>(L, nsweeps, rank1, all_smem); break;
+    default: k_relax_small<16><<<1, threads, smem, st>>>(L, nsweeps, rank1, all_smem); break;
   }
   ++g_launches;
 }

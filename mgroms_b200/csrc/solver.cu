@@ -647,6 +647,20 @@ int mgb_set_param(const char* key, const char* value) {
 }
 int mgb_reset_params(void) { g_params = Params(); g_overrides.clear(); return 0; }
 
+int mgb_namelist_probe(const char* path, char* out, int cap) {
+  Params P; std::string m;
+  int rc = namelist_read((path && path[0]) ? path : "nh_namelist", P, m);
+  if (rc < 0) return fail(m);
+  for (auto& kv : g_overrides) if (namelist_set(P, kv.first.c_str(), kv.second.c_str(), m) != 0) return fail(m);
+  char buf[1024];
+  std::snprintf(buf, sizeof buf, "solver_prec=%.17g;solver_maxiter=%d;nsmall=%d;ns_coarsest=%d;ns_pre=%d;ns_post=%d;cmatrix=%s;relax_method=%s;"
+                "interp_type=%s;restrict_type=%s;netcdf_output=%d;aggressive=%d;bmask=%d;file=%d",
+                P.solver_prec, P.solver_maxiter, P.nsmall, P.ns_coarsest, P.ns_pre, P.ns_post, P.cmatrix.c_str(), P.relax_method.c_str(),
+                P.interp_type.c_str(), P.restrict_type.c_str(), (int)P.netcdf_output, (int)P.aggressive, (int)P.bmask, rc == 0 ? 1 : 0);
+  std::strncpy(out, buf, cap); if (cap > 0) out[cap - 1] = 0;
+  return 0;
+}
+
 int mgb_plan_levels(int nx, int ny, int nz, int npx, int npy, int rank) {
   std::string m; Params P = g_params;
   if (plan_levels(P, nx, ny, nz, npx, npy, rank, g_plan, m) != 0) return fail(m);

@@ -48,6 +48,7 @@ def load(build_if_missing: bool = True):
     L.mgb_init.argtypes = [C.c_int] * 6 + [C.c_char_p, C.c_int]
     L.mgb_set_param.argtypes = [C.c_char_p, C.c_char_p]
     L.mgb_plan_levels.argtypes = [C.c_int] * 6
+    L.mgb_namelist_probe.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
     L.mgb_level_info.argtypes = [C.c_int, C.POINTER(C.c_int)]
     L.mgb_gather_members.argtypes = [C.c_int, C.POINTER(C.c_int)]
     L.mgb_comm_unique_id.argtypes = [C.c_void_p]
@@ -109,6 +110,13 @@ def set_params(**kw):
 
 def reset_params():
     _chk(load().mgb_reset_params())
+
+
+def namelist_probe(path=None) -> dict:
+    """Parse a namelist file exactly as nhydro_init would (host only) and return the 13 keys."""
+    buf = C.create_string_buffer(1024)
+    _chk(load().mgb_namelist_probe((path or "").encode(), buf, 1024))
+    return dict(kv.split("=", 1) for kv in buf.value.decode().split(";"))
 
 
 # ---- the five procedures of module nhydro -------------------------------------------------------------------
