@@ -1,0 +1,95 @@
+"""Multi-GPU parity: one process per GPU (NCCL halo exchange, all-reduce, mg_gather), compared with the CPU oracle run
+with the SAME npx x npy decomposition (a 1-rank and an N-rank reference legitimately differ).
+Needs >= 2 GPUs; run with `gpurun --gpus 2|4 -- python -m pytest tests/test_gpu_multi.py -m gpu`."""
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _ngpu():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, cfg, out):
+    import torch
+    import torch.distributed as dist
+    from mgroms_b200 import nhydro as nh
+    from common import geometry, velocities
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        kind, nx, ny, nz, npx, npy, params, uvw = cfg
+        nh.reset_params(); nh.set_params(**params)
+        nh.nhydro_init(nx, ny, nz, npx, npy, rank, device=rank)
+        box = [nh.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        nh.comm_init(box[0])
+        (dx, dy, zeta, h), vert = geometry(kind, nx, ny, nz, npx, npy, rank)
+        nh.nhydro_matrices(dx, dy, zeta, h, None, vert["hc"], vert["theta_b"], vert["theta_s"])
+        u, v, w = velocities(uvw, nx, ny, nz, npx, npy, rank)
+        nh.compute_rhs(None, u, v, w)
+        res = {"b": nh.get_field("b"), "cA": [nh.get_field("cA", l) for l in range(1, nh.nlevs() + 1)]}
+        nh.solve_p()
+        res["hist"] = nh.history()[0]; res["p"] = nh.get_field("p")
+        nh.correct_uvw(u, v, w); res["u"] = u
+        nh.nhydro_clean()
+        out.put((rank, res))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        out.put((rank, "ERR " + traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def run_world(cfg):
+    import torch.multiprocessing as mp
+    world = cfg[4] * cfg[5]
+    ctx = mp.get_context("spawn"); out = ctx.Queue(); port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, cfg, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(out.get(timeout=600) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    for r, v in res.items():
+        assert not isinstance(v, str), v
+    return res
+
+
+CFGS = [
+    ("seamount", 32, 32, 16, 2, 1, dict(solver_prec=1e-10, solver_maxiter=20), "wminus1"),
+    ("rndtopo", 16, 32, 16, 2, 1, dict(solver_prec=1e-10, solver_maxiter=20, nsmall=16), "random"),     # gathered coarse levels
+    ("seamount", 16, 16, 16, 2, 2, dict(solver_prec=1e-10, solver_maxiter=20), "random"),
+    ("cuc", 16, 32, 8, 2, 2, dict(solver_prec=1e-9, solver_maxiter=20, nsmall=16), "wminus1"),
+]
+
+
+@pytest.mark.parametrize("cfg", CFGS)
+def test_multi_gpu_matches_oracle_with_same_decomposition(cfg):
+    kind, nx, ny, nz, npx, npy, params, uvw = cfg
+    if _ngpu() < npx * npy:
+        pytest.skip(f"needs {npx * npy} GPUs")
+    from common import history_close, relerr
+    from oracle.pyoracle import make_case
+    o = make_case(kind, nx, ny, nz, npx, npy, uvw=uvw, relax_order=1, **params)
+    o.compute_rhs()
+    b_or = [o.get("b", 1, r) for r in range(npx * npy)]
+    o.solve_p(); o.correct_uvw()
+    res = run_world(cfg)
+    for r in range(npx * npy):
+        for lev in range(1, o.nlevs + 1):
+            assert np.array_equal(res[r]["cA"][lev - 1], o.get("cA", lev, r)), (r, lev)
+        assert np.array_equal(res[r]["b"][1:-1, 1:-1], b_or[r][1:-1, 1:-1]), r
+        history_close(res[r]["hist"], o.history()[0], rtol=1e-12, floor=1e-16)
+        assert relerr(res[r]["p"], o.get("p", 1, r)) < 1e-11, r
+        assert relerr(res[r]["u"], o.get_uvw(r)[0]) < 1e-10, r
