@@ -27,6 +27,7 @@ struct ColourSet {     // columns visited by one colour of a sweep
   int rb, jfix;
   int bottom_mode;     // 0: no k=1 diagonal terms ('simple');  1: rank-1 form (two (i+1) terms from the x1 snapshot);
                        // 2: all four terms read from p (no same-colour coupling, four-colour)
+  int fuse_halo;       // 1: level without neighbour ranks -> the kernels write the Neumann halo themselves and keep x1 = p(1,:,:)
 };
 void launch_snapshot_x1(cudaStream_t st, const LevelView& L);
 void launch_relax_A(cudaStream_t st, const LevelView& L, const ColourSet& cs);

@@ -5,6 +5,7 @@
 #include "kernels.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 
 namespace mgb {
 
@@ -196,6 +197,23 @@ void launch_unpack_rows(cudaStream_t st, double* a, const double* buf, int nzl, 
 // =====================================================================================================
 // relaxation
 // =====================================================================================================
+// Store a freshly relaxed value and, on a level without lateral neighbour ranks, its homogeneous-Neumann mirror(s):
+// the halo cell next to an edge column (and the corner next to a corner column) takes the same value, which is what
+// fill_halo would copy afterwards (src/mg_mpi_exchange.f90:504-598).  Saves the separate halo launch per colour.
+__device__ __forceinline__ void store_mirrored(double* __restrict__ a, size_t idx, double v, int j, int i, int ny, int nx, size_t sj, size_t si, bool mirror) {
+  a[idx] = v;
+  if (!mirror) return;
+  const bool w = (i == 1), e = (i == nx), s = (j == 1), n = (j == ny);
+  if (w) a[idx - si] = v;
+  if (e) a[idx + si] = v;
+  if (s) a[idx - sj] = v;
+  if (n) a[idx + sj] = v;
+  if (w && s) a[idx - si - sj] = v;
+  if (w && n) a[idx - si + sj] = v;
+  if (e && s) a[idx + si - sj] = v;
+  if (e && n) a[idx + si + sj] = v;
+}
+
 // x1(j,i) = p(1,j,i) for every column incl. halo: snapshot of the bottom plane taken before a colour is updated
 __global__ void k_snapshot_x1(const double* __restrict__ p, double* __restrict__ x1, int nz, size_t ncols) {
   size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -315,27 +333,311 @@ __global__ void __launch_bounds__(256, 2) k_relax_A(LevelView L, ColourSet cs, i
     if (i > L.nx) continue;
     const int j = colour_jstart(cs, i) + 2 * (tile_j * TJ + cj);
     if (j > L.ny) continue;
-    pw[IDX3(k, j, i, nz, ny2)] = s_rhs[c * pitch + k];
+    store_mirrored(pw, IDX3(k, j, i, nz, ny2), s_rhs[c * pitch + k], j, i, L.ny, L.nx, sj, si, cs.fuse_halo && cs.bottom_mode != 1);
   }
 }
 
 static void relax_tiling(const LevelView& L, const ColourSet& cs, int& TI, int& TJ, int& nti, int& ntj, size_t& smem) {
   const int nyc = (L.ny + 1) / 2;                    // colour columns per visited i (upper bound)
   const int nvi = (L.nx - cs.istart) / cs.istep + 1; // visited i
-  int tc_max = 2048 / L.nz;                          // columns per CTA: aim at ~2048 points per tile (8 per thread)
+  static int tile_pts = 0;
+  if (!tile_pts) { const char* e = getenv("MGB_TILE_PTS"); tile_pts = e ? atoi(e) : 1024; }
+  int tc_max = tile_pts / L.nz;                      // columns per CTA: aim at ~2048 points per tile (8 per thread)
   if (tc_max < 16) tc_max = 16;
   if (tc_max > 1024) tc_max = 1024;
-  while (tc_max > 1 && (size_t)tc_max * (L.nz + 1) * 3 * sizeof(double) > 56 * 1024) tc_max /= 2;
+  while (tc_max > 1 && (size_t)tc_max * (L.nz + 1) * 3 * sizeof(double) > 100 * 1024) tc_max /= 2;
   while (tc_max * L.nz > 256 && ((size_t)nyc * nvi + tc_max - 1) / tc_max < 296) tc_max /= 2;   // small level: more, smaller tiles
   TJ = nyc < tc_max ? nyc : tc_max;
   TI = tc_max / TJ; if (TI < 1) TI = 1; if (TI > nvi) TI = nvi;
   ntj = (nyc + TJ - 1) / TJ; nti = (nvi + TI - 1) / TI;
   smem = (size_t)TI * TJ * (L.nz + 1) * 3 * sizeof(double);
 }
+// Kernel A, warp-autonomous variant: every WARP owns its own tile of TCW colour columns and runs the three phases
+// (k-parallel rhs -> per-column Thomas -> coalesced write-back) with __syncwarp only, so the warps of an SM are in
+// different phases at any time: no block barrier, no idle warps while one thread per column runs Thomas, and the
+// memory pipe always sees a number of warps with 27 loads per lane in flight.  Only rhs/x is staged in shared
+// memory ([TCW][nz+1] per warp); the Thomas thread reads its column's bet and cA(2) straight from global memory as
+// aligned double2 (each 128-byte line is consumed over 16 consecutive k, so it stays in L1).
+// Arithmetic is identical, operation by operation, to k_relax_A.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 512 / (WARPS * 32)) k_relax_A3(LevelView L, ColourSet cs, int TI, int TJ, int ntj, int ntiles) {
+  extern __shared__ __align__(16) double sm[];
+  const int nz = L.nz, ny2 = L.ny + 2, pitch = nz + 1;
+  const int TC = TI * TJ;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x * WARPS + warp;
+  if (tile >= ntiles) return;
+  double* s_x = sm + (size_t)warp * TC * pitch;
+  const int tile_j = tile % ntj, tile_i = tile / ntj;
+  const int sj = nz; const size_t si = (size_t)nz * ny2;
+  const double* __restrict__ p = L.p; const double* __restrict__ b = L.b;
+  const double* __restrict__ c2 = L.cA[1]; const double* __restrict__ c3 = L.cA[2]; const double* __restrict__ c4 = L.cA[3];
+  const double* __restrict__ c5 = L.cA[4]; const double* __restrict__ c6 = L.cA[5]; const double* __restrict__ c7 = L.cA[6];
+  const double* __restrict__ c8 = L.cA[7]; const double* __restrict__ bet = L.bet;
+
+  // ---- phase 1: rhs, lanes along k
+  const int nelem = TC * nz;
+  for (int e = lane; e < nelem; e += 32) {
+    const int k = e % nz, c = e / nz;
+    const int ci = c / TJ, cj = c % TJ;
+    const int i = cs.istart + (tile_i * TI + ci) * cs.istep;
+    if (i > L.nx) continue;
+    const int j = colour_jstart(cs, i) + 2 * (tile_j * TJ + cj);
+    if (j > L.ny) continue;
+    const size_t idx = IDX3(k, j, i, nz, ny2);
+    const double bb = b[idx];
+    const double a3 = c3[idx],           q3 = p[idx - sj + 1];
+    const double a3n = c3[idx + sj - 1], q3n = p[idx + sj - 1];
+    const double a4 = c4[idx],           q4 = p[idx - sj];
+    const double a4n = c4[idx + sj],     q4n = p[idx + sj];
+    const double a5 = c5[idx],           q5 = p[idx - sj - 1];
+    const double a5n = c5[idx + sj + 1], q5n = p[idx + sj + 1];
+    const double a6 = c6[idx],           q6 = p[idx - si + 1];
+    const double a6n = c6[idx + si - 1], q6n = p[idx + si - 1];
+    const double a7 = c7[idx],           q7 = p[idx - si];
+    const double a7n = c7[idx + si],     q7n = p[idx + si];
+    const double a8 = c8[idx],           q8 = p[idx - si - 1];
+    const double a8n = c8[idx + si + 1], q8n = p[idx + si + 1];
+    const bool lo = (k > 0), hi = (k < nz - 1);
+    double acc = bb;
+    if (hi) acc = acc - a3 * q3;
+    if (lo) acc = acc - a3n * q3n;
+    acc = acc - a4 * q4;
+    acc = acc - a4n * q4n;
+    if (lo) acc = acc - a5 * q5;
+    if (hi) acc = acc - a5n * q5n;
+    if (hi) acc = acc - a6 * q6;
+    if (lo) acc = acc - a6n * q6n;
+    acc = acc - a7 * q7;
+    acc = acc - a7n * q7n;
+    if (lo) acc = acc - a8 * q8;
+    if (hi) acc = acc - a8n * q8n;
+    if (k == 0) {
+      if (cs.bottom_mode == 1) {
+        const size_t c2d = (size_t)j + (size_t)ny2 * i;
+        acc = acc - L.c5b[c2d - 1 + ny2] * L.x1[c2d - 1 + ny2];
+        acc = acc - L.c8b[c2d + 1 + ny2] * L.x1[c2d + 1 + ny2];
+      } else if (cs.bottom_mode == 2) {
+        acc = acc - a5 * p[idx + sj - si];
+        acc = acc - c5[idx - sj + si] * p[idx - sj + si];
+        acc = acc - a8 * p[idx - sj - si];
+        acc = acc - c8[idx + sj + si] * p[idx + sj + si];
+      }
+    }
+    s_x[c * pitch + k] = acc;
+  }
+  __syncwarp();
+
+  // ---- phase 2: Thomas, one lane per column; bet and cA(2) as double2 from global (k even -> 16-byte aligned)
+  for (int c = lane; c < TC; c += 32) {
+    const int ci = c / TJ, cj = c % TJ;
+    const int i = cs.istart + (tile_i * TI + ci) * cs.istep;
+    if (i > L.nx) continue;
+    const int j = colour_jstart(cs, i) + 2 * (tile_j * TJ + cj);
+    if (j > L.ny) continue;
+    const size_t idx0 = IDX3(0, j, i, nz, ny2);
+    const double2* __restrict__ bt2 = reinterpret_cast<const double2*>(bet + idx0);
+    const double2* __restrict__ cc2 = reinterpret_cast<const double2*>(c2 + idx0);   // cc2[m] = (cA2(k=2m), cA2(k=2m+1)), 0-based k
+    double* x = s_x + c * pitch;
+    // forward: x(k) = (rhs(k) - ud(k-1) x(k-1)) bet(k), ud(k-1) = cA2(k)
+    double xm = 0.0;
+#pragma unroll 4
+    for (int m = 0; m < nz / 2; ++m) {
+      const double2 bt = bt2[m], cc = cc2[m];
+      xm = (m == 0) ? x[0] * bt.x : (x[2 * m] - cc.x * xm) * bt.x;
+      x[2 * m] = xm;
+      xm = (x[2 * m + 1] - cc.y * xm) * bt.y;
+      x[2 * m + 1] = xm;
+    }
+    // backward: x(k) -= (ud(k) bet(k)) x(k+1), ud(k) = cA2(k+1)
+#pragma unroll 4
+    for (int m = nz / 2 - 1; m >= 0; --m) {
+      const double2 bt = bt2[m], cc = cc2[m];
+      if (m < nz / 2 - 1) { const double cnext = c2[idx0 + 2 * m + 2]; xm = x[2 * m + 1] - (cnext * bt.y) * xm; x[2 * m + 1] = xm; }
+      xm = x[2 * m] - (cc.y * bt.x) * xm;
+      x[2 * m] = xm;
+    }
+    if (cs.bottom_mode == 1) L.q1[(size_t)j + (size_t)ny2 * i] = xm;
+  }
+  __syncwarp();
+
+  // ---- phase 3: write back, lanes along k
+  double* __restrict__ pw = L.p;
+  for (int e = lane; e < nelem; e += 32) {
+    const int k = e % nz, c = e / nz;
+    const int ci = c / TJ, cj = c % TJ;
+    const int i = cs.istart + (tile_i * TI + ci) * cs.istep;
+    if (i > L.nx) continue;
+    const int j = colour_jstart(cs, i) + 2 * (tile_j * TJ + cj);
+    if (j > L.ny) continue;
+    pw[IDX3(k, j, i, nz, ny2)] = s_x[c * pitch + k];
+  }
+}
+// Kernel A, warp-specialised persistent variant.  A CTA of 8 warps loops over tiles with two shared-memory tile
+// buffers: warps 0..6 ("producers") run phase 1 (27 loads per lane in flight, rhs/bet/ud -> smem buffer) and the coalesced
+// write-back of the tile solved two steps earlier, warp 7 ("solver") only runs Thomas (one lane per column).  Named
+// barriers (bar.sync / bar.arrive) hand the buffers over, so producers never idle behind the serial Thomas phase and
+// the memory pipe is fed continuously.  Same arithmetic, operation by operation, as k_relax_A.
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+__global__ void __launch_bounds__(256, 2) k_relax_A4(LevelView L, ColourSet cs, int TI, int TJ, int ntj, int ntiles) {
+  extern __shared__ __align__(16) double sm[];
+  const int nz = L.nz, ny2 = L.ny + 2, pitch = nz + 1;
+  const int TC = TI * TJ;
+  const size_t bufsz = (size_t)3 * TC * pitch;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sj = nz; const size_t si = (size_t)nz * ny2;
+  const int nelem = TC * nz;
+  constexpr int NPROD = 7 * 32;
+  // barrier ids: 1,2 = buffer b full ; 3,4 = buffer b empty
+  if (warp < 7) {
+    const double* __restrict__ p = L.p; const double* __restrict__ b = L.b;
+    const double* __restrict__ c2 = L.cA[1]; const double* __restrict__ c3 = L.cA[2]; const double* __restrict__ c4 = L.cA[3];
+    const double* __restrict__ c5 = L.cA[4]; const double* __restrict__ c6 = L.cA[5]; const double* __restrict__ c7 = L.cA[6];
+    const double* __restrict__ c8 = L.cA[7]; const double* __restrict__ bet = L.bet;
+    double* __restrict__ pw = L.p;
+    auto writeback = [&](const double* s_x, int t) {         // coalesced along k; final values also go to the Neumann halo
+      const int t_j = t % ntj, t_i = t / ntj;
+      for (int e = threadIdx.x; e < nelem; e += NPROD) {
+        const int k = e % nz, c = e / nz;
+        const int ci = c / TJ, cj = c % TJ;
+        const int i = cs.istart + (t_i * TI + ci) * cs.istep;
+        if (i > L.nx) continue;
+        const int j = colour_jstart(cs, i) + 2 * (t_j * TJ + cj);
+        if (j > L.ny) continue;
+        store_mirrored(pw, IDX3(k, j, i, nz, ny2), s_x[c * pitch + k], j, i, L.ny, L.nx, sj, si, cs.fuse_halo && cs.bottom_mode != 1);
+      }
+    };
+    int n = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
+      const int bsel = n & 1;
+      double* s_rhs = sm + bsel * bufsz; double* s_bet = s_rhs + (size_t)TC * pitch; double* s_ud = s_bet + (size_t)TC * pitch;
+      if (n >= 2) {                                         // tile n-2 sits solved in this buffer: write it back, then reuse the buffer
+        named_bar_sync(3 + bsel, 256);
+        writeback(s_rhs, tile - 2 * (int)gridDim.x);
+        named_bar_sync(5, NPROD);
+      }
+      const int tile_j = tile % ntj, tile_i = tile / ntj;
+      for (int e = threadIdx.x; e < nelem; e += NPROD) {
+        const int k = e % nz, c = e / nz;
+        const int ci = c / TJ, cj = c % TJ;
+        const int i = cs.istart + (tile_i * TI + ci) * cs.istep;
+        if (i > L.nx) continue;
+        const int j = colour_jstart(cs, i) + 2 * (tile_j * TJ + cj);
+        if (j > L.ny) continue;
+        const size_t idx = IDX3(k, j, i, nz, ny2);
+        const double bb = b[idx], bt = bet[idx], udv = c2[idx + 1];
+        const double a3 = c3[idx],           q3 = p[idx - sj + 1];
+        const double a3n = c3[idx + sj - 1], q3n = p[idx + sj - 1];
+        const double a4 = c4[idx],           q4 = p[idx - sj];
+        const double a4n = c4[idx + sj],     q4n = p[idx + sj];
+        const double a5 = c5[idx],           q5 = p[idx - sj - 1];
+        const double a5n = c5[idx + sj + 1], q5n = p[idx + sj + 1];
+        const double a6 = c6[idx],           q6 = p[idx - si + 1];
+        const double a6n = c6[idx + si - 1], q6n = p[idx + si - 1];
+        const double a7 = c7[idx],           q7 = p[idx - si];
+        const double a7n = c7[idx + si],     q7n = p[idx + si];
+        const double a8 = c8[idx],           q8 = p[idx - si - 1];
+        const double a8n = c8[idx + si + 1], q8n = p[idx + si + 1];
+        const bool lo = (k > 0), hi = (k < nz - 1);
+        double acc = bb;
+        if (hi) acc = acc - a3 * q3;
+        if (lo) acc = acc - a3n * q3n;
+        acc = acc - a4 * q4;
+        acc = acc - a4n * q4n;
+        if (lo) acc = acc - a5 * q5;
+        if (hi) acc = acc - a5n * q5n;
+        if (hi) acc = acc - a6 * q6;
+        if (lo) acc = acc - a6n * q6n;
+        acc = acc - a7 * q7;
+        acc = acc - a7n * q7n;
+        if (lo) acc = acc - a8 * q8;
+        if (hi) acc = acc - a8n * q8n;
+        if (k == 0) {
+          if (cs.bottom_mode == 1) {
+            const size_t c2d = (size_t)j + (size_t)ny2 * i;
+            acc = acc - L.c5b[c2d - 1 + ny2] * L.x1[c2d - 1 + ny2];
+            acc = acc - L.c8b[c2d + 1 + ny2] * L.x1[c2d + 1 + ny2];
+          } else if (cs.bottom_mode == 2) {
+            acc = acc - a5 * p[idx + sj - si];
+            acc = acc - c5[idx - sj + si] * p[idx - sj + si];
+            acc = acc - a8 * p[idx - sj - si];
+            acc = acc - c8[idx + sj + si] * p[idx + sj + si];
+          }
+        }
+        s_rhs[c * pitch + k] = acc;
+        s_bet[c * pitch + k] = bt;
+        s_ud[c * pitch + k] = hi ? udv : 0.0;
+      }
+      __threadfence_block();
+      named_bar_arrive(1 + bsel, 256);                      // buffer full
+    }
+    // drain: the last (up to two) tiles of this CTA
+    for (int m = (n >= 2 ? n - 2 : 0); m < n; ++m) {
+      const int bsel = m & 1;
+      named_bar_sync(3 + bsel, 256);
+      writeback(sm + bsel * bufsz, (int)blockIdx.x + m * (int)gridDim.x);
+    }
+  } else {
+    int n = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
+      const int bsel = n & 1;
+      double* s_rhs = sm + bsel * bufsz; const double* s_bet = s_rhs + (size_t)TC * pitch; const double* s_ud = s_bet + (size_t)TC * pitch;
+      named_bar_sync(1 + bsel, 256);                        // wait for the producers
+      const int tile_j = tile % ntj, tile_i = tile / ntj;
+      for (int c = lane; c < TC; c += 32) {
+        const int ci = c / TJ, cj = c % TJ;
+        const int i = cs.istart + (tile_i * TI + ci) * cs.istep;
+        if (i > L.nx) continue;
+        const int j = colour_jstart(cs, i) + 2 * (tile_j * TJ + cj);
+        if (j > L.ny) continue;
+        double* x = s_rhs + c * pitch; const double* bt = s_bet + c * pitch; const double* ud = s_ud + c * pitch;
+        double xm = x[0] * bt[0];
+        x[0] = xm;
+        for (int k = 1; k < nz; ++k) { xm = (x[k] - ud[k - 1] * xm) * bt[k]; x[k] = xm; }
+        for (int k = nz - 2; k >= 0; --k) { xm = x[k] - (ud[k] * bt[k]) * xm; x[k] = xm; }
+        if (cs.bottom_mode == 1) L.q1[(size_t)j + (size_t)ny2 * i] = xm;
+      }
+      __syncwarp();
+      __threadfence_block();
+      named_bar_arrive(3 + bsel, 256);                      // solved: the producers write it back
+    }
+  }
+}
+static void relax_tiling3(const LevelView& L, const ColourSet& cs, int& TI, int& TJ, int& nti, int& ntj) {
+  const int nyc = (L.ny + 1) / 2;
+  const int nvi = (L.nx - cs.istart) / cs.istep + 1;
+  int tc = 2048 / L.nz; if (tc > 32) tc = 32; if (tc < 8) tc = 8;          // columns per warp tile
+  while (tc > 8 && ((size_t)nyc * nvi + tc - 1) / tc < 148 * 12) tc /= 2;   // small level: more, smaller tiles
+  TJ = nyc < tc ? nyc : tc;
+  TI = tc / TJ; if (TI < 1) TI = 1; if (TI > nvi) TI = nvi;
+  ntj = (nyc + TJ - 1) / TJ; nti = (nvi + TI - 1) / TI;
+}
 void launch_relax_A(cudaStream_t st, const LevelView& L, const ColourSet& cs) {
+  static int variant = -1;
+  if (variant < 0) { const char* e = getenv("MGB_RELAX_A"); variant = e ? atoi(e) : 4; }
+  if (variant == 3) {
+    int TI, TJ, nti, ntj;
+    relax_tiling3(L, cs, TI, TJ, nti, ntj);
+    const int ntiles = nti * ntj;
+    const size_t smem = (size_t)4 * TI * TJ * (L.nz + 1) * sizeof(double);
+    k_relax_A3<4><<<(ntiles + 3) / 4, 128, smem, st>>>(L, cs, TI, TJ, ntj, ntiles); ++g_launches;
+    return;
+  }
+  if (variant == 4) {
+    int TI, TJ, nti, ntj; size_t smem1;
+    relax_tiling(L, cs, TI, TJ, nti, ntj, smem1);
+    const int ntiles = nti * ntj;
+    int grid = ntiles < 296 ? ntiles : 296;
+    k_relax_A4<<<grid, 256, 2 * smem1, st>>>(L, cs, TI, TJ, ntj, ntiles); ++g_launches;
+    return;
+  }
   int TI, TJ, nti, ntj; size_t smem;
   relax_tiling(L, cs, TI, TJ, nti, ntj, smem);
-  k_relax_A<<<nti * ntj, 256, smem, st>>>(L, cs, TI, TJ, ntj); ++g_launches;
+  static int nthr = 0;
+  if (!nthr) { const char* e = getenv("MGB_A_THREADS"); nthr = e ? atoi(e) : 256; }
+  k_relax_A<<<nti * ntj, nthr, smem, st>>>(L, cs, TI, TJ, ntj); ++g_launches;
 }
 
 // Kernel B: the sequential part of the red-black bottom coupling, on the 2-D k=1 plane only.
@@ -426,7 +728,9 @@ __global__ void __launch_bounds__(256) k_relax_C(LevelView L, ColourSet cs, int 
   if (j > L.ny) return;
   const double sv = L.s[(size_t)j + (size_t)ny2 * i];
   const size_t idx = IDX3(k, j, i, nz, ny2);
-  L.p[idx] = L.p[idx] + sv * L.g[idx];
+  const double v = L.p[idx] + sv * L.g[idx];
+  store_mirrored(L.p, idx, v, j, i, L.ny, L.nx, (size_t)nz, (size_t)nz * ny2, cs.fuse_halo != 0);
+  if (k == 0 && cs.fuse_halo) store_mirrored(L.x1, (size_t)j + (size_t)ny2 * i, v, j, i, L.ny, L.nx, 1, (size_t)ny2, true);
 }
 void launch_relax_C(cudaStream_t st, const LevelView& L, const ColourSet& cs) {
   const int nyc = (L.ny + 1) / 2;
@@ -567,6 +871,8 @@ __global__ void __launch_bounds__(1024) k_relax_small(LevelView L, int nsweeps, 
 }
 void kernels_init() {
   cudaFuncSetAttribute(k_relax_A, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_relax_A3<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_relax_A4, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_relax_B<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   cudaFuncSetAttribute(k_relax_B<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   cudaFuncSetAttribute(k_relax_B<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
@@ -615,7 +921,7 @@ __device__ __forceinline__ double block_sum_256(double v, double* s_red) {
 }
 
 // one block handles a chunk of one i-slab: elements (k, j) flattened, j = 1..ny
-__global__ void __launch_bounds__(256, 2) k_residual(LevelView L, int real_matrix, int chunks_per_i, double* __restrict__ partials) {
+__global__ void __launch_bounds__(256, 3) k_residual(LevelView L, int real_matrix, int chunks_per_i, double* __restrict__ partials) {
   __shared__ double s_red[8];
   const int nz = L.nz, ny = L.ny, ny2 = ny + 2;
   const int i = 1 + blockIdx.x / chunks_per_i, chunk = blockIdx.x % chunks_per_i;

@@ -96,6 +96,7 @@ struct Solver {
   bool fused_prolong = true;
   bool use_small = true;             // fused single-CTA relaxation on small neighbour-free levels
   bool use_graph = true;             // replay one captured F-cycle (+ residual) per outer iteration
+  bool fuse_halo = true;             // neighbour-free levels: relax kernels write the Neumann halo themselves
   cudaGraphExec_t cycle_graph = nullptr;
   long long cycle_graph_nodes = 0;
   int nlevs() const { return (int)L.size(); }
@@ -216,22 +217,25 @@ static int relax(int lev, int nsweeps) {
       launch_relax_small(S.st, g.v, nsweeps, (real_matrix && g.bottom_diag) ? 1 : 0);
       return 0;
     }
+    const bool rank1 = real_matrix && g.bottom_diag;
+    const int fuse = (lonely && S.fuse_halo) ? 1 : 0;
+    if (fuse && rank1) launch_snapshot_x1(S.st, g.v);        // x1 = p(1,:,:) once; kernel C keeps it current afterwards
     for (int it = 0; it < nsweeps; ++it)
       for (int rb = 1; rb <= 2; ++rb) {
-        ColourSet cs{1, 1, 0, rb, 0, 0};
-        const bool rank1 = real_matrix && g.bottom_diag;
-        cs.bottom_mode = rank1 ? 1 : 0;
-        if (rank1) launch_snapshot_x1(S.st, g.v);
+        ColourSet cs{1, 1, 0, rb, 0, rank1 ? 1 : 0, fuse};
+        if (rank1 && !fuse) launch_snapshot_x1(S.st, g.v);
         launch_relax_A(S.st, g.v, cs);
         if (rank1) { launch_relax_B(S.st, g.v, cs); launch_relax_C(S.st, g.v, cs); }
-        RC(fill_halo(lev, g.v.p, g.d.nz, 1));
+        if (!fuse) RC(fill_halo(lev, g.v.p, g.d.nz, 1));
       }
   } else if (m == "Four-Color" || m == "FC") {
     for (int it = 0; it < nsweeps; ++it)
       for (int fc1 = 1; fc1 <= 2; ++fc1) for (int fc2 = 1; fc2 <= 2; ++fc2) {
-        ColourSet cs{1 + (fc1 - 1) % 2, 2, 1, 0, 1 + (fc2 - 1) % 2, real_matrix ? 2 : 0};
+        bool alone = true; for (int q = 0; q < 8; ++q) alone &= g.d.neighb[q] < 0;
+        const int fuse = (alone && S.fuse_halo) ? 1 : 0;
+        ColourSet cs{1 + (fc1 - 1) % 2, 2, 1, 0, 1 + (fc2 - 1) % 2, real_matrix ? 2 : 0, fuse};
         if (cs.istart <= g.d.nx && cs.jfix <= g.d.ny) launch_relax_A(S.st, g.v, cs);
-        RC(fill_halo(lev, g.v.p, g.d.nz, 1));
+        if (!fuse) RC(fill_halo(lev, g.v.p, g.d.nz, 1));
       }
   } else {
     return fail("relax_method '" + m + "' is not built (RB and FC are; GS is listed under SURVEY 8f-4)");
@@ -595,6 +599,8 @@ static int init(int nx, int ny, int nz, int npx, int npy, int rank, const char* 
   S.fused_prolong = !(ex && ex[0] == '1');
   const char* ns = std::getenv("MGB_NO_SMALL_KERNEL");
   S.use_small = !(ns && ns[0] == '1');
+  const char* nf = std::getenv("MGB_NO_FUSED_HALO");
+  S.fuse_halo = !(nf && nf[0] == '1');
   const char* ng = std::getenv("MGB_NO_GRAPH");
   S.use_graph = !(ng && ng[0] == '1');
   kernels_init();
@@ -824,11 +830,13 @@ int mgb_profile_level1(int reps, double* out4) {
     const int n = pass == 0 ? 2 : reps;
     CU(cudaEventRecord(a, S.st));
     for (int r = 0; r < n; ++r) {
-      ColourSet cs{1, 1, 0, 1 + (r & 1), 0, rank1 ? 1 : 0};
-      if (rank1) launch_snapshot_x1(S.st, g.v);
+      bool alone = true; for (int q = 0; q < 8; ++q) alone &= g.d.neighb[q] < 0;
+      const int fuse = (alone && S.fuse_halo) ? 1 : 0;
+      ColourSet cs{1, 1, 0, 1 + (r & 1), 0, rank1 ? 1 : 0, fuse};
+      if (rank1 && (!fuse || r == 0)) launch_snapshot_x1(S.st, g.v);
       launch_relax_A(S.st, g.v, cs);
       if (rank1) { launch_relax_B(S.st, g.v, cs); launch_relax_C(S.st, g.v, cs); }
-      RC(fill_halo(1, g.v.p, g.d.nz, 1));
+      if (!fuse) RC(fill_halo(1, g.v.p, g.d.nz, 1));
     }
     CU(cudaEventRecord(b, S.st)); CU(cudaEventSynchronize(b)); CU(cudaEventElapsedTime(&ms, a, b));
     out4[0] = ms / n;
