@@ -743,13 +743,13 @@ void launch_relax_C(cudaStream_t st, const LevelView& L, const ColourSet& cs) {
 // correction and the Neumann halo of p) in ONE launch of ONE CTA.  Coarse levels are launch/latency bound: this
 // replaces 10*nsweeps launches by one.  Only valid when the level has no lateral neighbour rank (single GPU, or
 // a level gathered onto one rank).  Same arithmetic, operation by operation, as kernels A/B/C + halo.
-//   shared memory: five 2-D planes (x1, q1, c5b, c8b, g1) of (ny+2)*(nx+2) doubles + per-warp x1 rows
+//   shared memory: six 2-D planes (x1, q1, c5b, c8b, g1, s) of (ny+2)*(nx+2) doubles + per-warp x1 rows
 template <int NZ>
 __global__ void __launch_bounds__(1024) k_relax_small(LevelView L, int nsweeps, int rank1, int all_smem) {
   extern __shared__ __align__(16) double sm[];
   const int nx = L.nx, ny = L.ny, ny2 = ny + 2, nyc = ny / 2;
   const int n2 = ny2 * (nx + 2);
-  double *x1 = sm, *q1 = sm + n2, *c5b = sm + 2 * n2, *c8b = sm + 3 * n2, *g1 = sm + 4 * n2, *rows = sm + 5 * n2;   // rows: [8 warps][2][ny2]
+  double *x1 = sm, *q1 = sm + n2, *c5b = sm + 2 * n2, *c8b = sm + 3 * n2, *g1 = sm + 4 * n2, *ss = sm + 5 * n2, *rows = sm + 6 * n2;   // rows: [8 warps][2][ny2]
   const int sj = NZ; const int si = NZ * ny2;
   // the 3-D operands stay in global memory (L2) or, when the whole level fits (all_smem), are staged in shared memory
   double* p = L.p;
@@ -765,8 +765,10 @@ __global__ void __launch_bounds__(1024) k_relax_small(LevelView L, int nsweeps, 
   }
   if (rank1) for (int e = threadIdx.x; e < n2; e += blockDim.x) { c5b[e] = L.c5b[e]; c8b[e] = L.c8b[e]; g1[e] = L.g1[e]; }
   __syncthreads();
+  // x1 = p(1,:,:) once; afterwards the final stores of each colour keep it (and the Neumann halo of p) current
+  if (rank1) { for (int e = threadIdx.x; e < n2; e += blockDim.x) x1[e] = p[(size_t)e * NZ]; __syncthreads(); }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   for (int it = 0; it < nsweeps; ++it) for (int rb = 1; rb <= 2; ++rb) {
-    if (rank1) { for (int e = threadIdx.x; e < n2; e += blockDim.x) x1[e] = p[(size_t)e * NZ]; __syncthreads(); }
     // ---- A: thread per column
     for (int c = threadIdx.x; c < nx * nyc; c += blockDim.x) {
       const int i = 1 + c / nyc, jc = c % nyc;
@@ -802,21 +804,41 @@ __global__ void __launch_bounds__(1024) k_relax_small(LevelView L, int nsweeps, 
       for (int k = 1; k < NZ; ++k) { xm = (x[k] - c2[idx0 + k] * xm) * bet[idx0 + k]; x[k] = xm; }
 #pragma unroll
       for (int k = NZ - 2; k >= 0; --k) { xm = x[k] - (c2[idx0 + k + 1] * bet[idx0 + k]) * xm; x[k] = xm; }
+      if (rank1) {            // not final yet: q only
 #pragma unroll
-      for (int k = 0; k < NZ; ++k) p[idx0 + k] = x[k];
-      if (rank1) q1[j + ny2 * i] = xm;
+        for (int k = 0; k < NZ; ++k) p[idx0 + k] = x[k];
+        q1[j + ny2 * i] = xm;
+      } else {                // final value of this colour: also its Neumann mirrors
+#pragma unroll
+        for (int k = 0; k < NZ; ++k) store_mirrored(p, (size_t)(idx0 + k), x[k], j, i, ny, nx, (size_t)sj, (size_t)si, true);
+      }
     }
     __syncthreads();
     if (rank1) {
-      // ---- B: chunked bottom recurrence, one warp per chunk (same chunks and warm-up as kernel B)
-      {
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-        const int wpar = nwarps < 8 ? nwarps : 8;
-        const int nchunks = (nx + L.rb_chunk - 1) / L.rb_chunk;
-        if (warp < wpar) {
-          double* prev = rows + warp * 2 * ny2; double* cur = prev + ny2;
-          for (int c = warp; c < nchunks; c += wpar) {
-            const int c0 = 1 + c * L.rb_chunk, c1 = min(nx, c0 + L.rb_chunk - 1), i0 = max(1, c0 - L.rb_W);
+      // ---- B: chunked bottom recurrence, one warp per chunk (same chunks and warm-up as kernel B).  When the colour's
+      //      columns of a row fit one warp (ny <= 64) the previous row lives in registers and travels by shuffles.
+      const int wpar = nwarps < 8 ? nwarps : 8;
+      const int nchunks = (nx + L.rb_chunk - 1) / L.rb_chunk;
+      if (warp < wpar) {
+        for (int c = warp; c < nchunks; c += wpar) {
+          const int c0 = 1 + c * L.rb_chunk, c1 = min(nx, c0 + L.rb_chunk - 1), i0 = max(1, c0 - L.rb_W);
+          if (nyc <= 32) {
+            const bool act = lane < nyc;
+            const int l = act ? lane : 0;
+            int js = 1 + ((i0 + rb) & 1);
+            double xv = x1[(3 - js) + 2 * l + ny2 * (i0 - 1)];               // x1 at the colour's positions of row i0-1
+            for (int i = i0; i <= c1; ++i, js = 3 - js) {
+              const double up = __shfl_up_sync(0xffffffffu, xv, 1), dn = __shfl_down_sync(0xffffffffu, xv, 1);
+              const double h0 = x1[ny2 * (i - 1)], hN = x1[ny + 1 + ny2 * (i - 1)];
+              const int j = js + 2 * l, c2d = j + ny2 * i;
+              double xp, xmn;                                                // x1(j+1,i-1), x1(j-1,i-1)
+              if (js == 1) { xp = xv; xmn = (l == 0) ? h0 : up; } else { xmn = xv; xp = (l == nyc - 1) ? hN : dn; }
+              const double sv = -(c5b[c2d] * xp + c8b[c2d] * xmn);
+              xv = q1[c2d] + sv * g1[c2d];
+              if (act && i >= c0) ss[c2d] = sv;
+            }
+          } else {
+            double* prev = rows + warp * 2 * ny2; double* cur = prev + ny2;
             for (int j = lane; j < ny2; j += 32) prev[j] = x1[j + ny2 * (i0 - 1)];
             __syncwarp();
             for (int i = i0; i <= c1; ++i) {
@@ -825,7 +847,7 @@ __global__ void __launch_bounds__(1024) k_relax_small(LevelView L, int nsweeps, 
                 const int j = js + 2 * jc, c2d = j + ny2 * i;
                 const double sv = -(c5b[c2d] * prev[j + 1] + c8b[c2d] * prev[j - 1]);
                 cur[j] = q1[c2d] + sv * g1[c2d];
-                if (i >= c0) L.s[c2d] = sv;
+                if (i >= c0) ss[c2d] = sv;
               }
               if (lane == 0) { cur[0] = x1[ny2 * i]; cur[ny + 1] = x1[ny + 1 + ny2 * i]; }
               __syncwarp();
@@ -835,37 +857,21 @@ __global__ void __launch_bounds__(1024) k_relax_small(LevelView L, int nsweeps, 
         }
       }
       __syncthreads();
-      // ---- C: p += s g on the colour's columns
+      // ---- C: p += s g on the colour's columns; final values -> Neumann mirrors and the x1 plane
       for (int c = threadIdx.x; c < nx * nyc; c += blockDim.x) {
         const int i = 1 + c / nyc, jc = c % nyc;
         const int j = 1 + ((i + rb) & 1) + 2 * jc;
         const int idx0 = NZ * (j + ny2 * i);
-        const double sv = L.s[j + ny2 * i];
+        const double sv = ss[j + ny2 * i];
 #pragma unroll
-        for (int k = 0; k < NZ; ++k) p[idx0 + k] = p[idx0 + k] + sv * g[idx0 + k];
+        for (int k = 0; k < NZ; ++k) {
+          const double v = p[idx0 + k] + sv * g[idx0 + k];
+          store_mirrored(p, (size_t)(idx0 + k), v, j, i, ny, nx, (size_t)sj, (size_t)si, true);
+          if (k == 0) store_mirrored(x1, (size_t)(j + ny2 * i), v, j, i, ny, nx, 1, (size_t)ny2, true);
+        }
       }
       __syncthreads();
     }
-    // ---- halo of p: homogeneous Neumann on all four sides + corners
-    for (int e = threadIdx.x; e < 2 * ny * NZ; e += blockDim.x) {
-      const int side = e / (ny * NZ), rem = e % (ny * NZ);
-      if (side == 0) p[NZ * (1 + ny2 * 0) + rem] = p[NZ * (1 + ny2 * 1) + rem];
-      else p[NZ * (1 + ny2 * (nx + 1)) + rem] = p[NZ * (1 + ny2 * nx) + rem];
-    }
-    for (int e = threadIdx.x; e < 2 * nx * NZ; e += blockDim.x) {
-      const int side = e / (nx * NZ), rem = e % (nx * NZ);
-      const int i = 1 + rem / NZ, k = rem % NZ;
-      if (side == 0) p[k + NZ * (0 + ny2 * i)] = p[k + NZ * (1 + ny2 * i)];
-      else p[k + NZ * (ny + 1 + ny2 * i)] = p[k + NZ * (ny + ny2 * i)];
-    }
-    for (int e = threadIdx.x; e < 4 * NZ; e += blockDim.x) {
-      const int cc = e / NZ, k = e % NZ;
-      if (cc == 0) p[k + NZ * (0 + ny2 * 0)] = p[k + NZ * (1 + ny2 * 1)];
-      if (cc == 1) p[k + NZ * (0 + ny2 * (nx + 1))] = p[k + NZ * (1 + ny2 * nx)];
-      if (cc == 2) p[k + NZ * (ny + 1 + ny2 * (nx + 1))] = p[k + NZ * (ny + ny2 * nx)];
-      if (cc == 3) p[k + NZ * (ny + 1 + ny2 * 0)] = p[k + NZ * (ny + ny2 * 1)];
-    }
-    __syncthreads();
   }
   if (all_smem) for (int e = threadIdx.x; e < n3; e += blockDim.x) L.p[e] = p[e];
 }
@@ -889,7 +895,7 @@ bool relax_small_supported(const LevelView& L) {
 }
 void launch_relax_small(cudaStream_t st, const LevelView& L, int nsweeps, int rank1) {
   const size_t n2 = (size_t)(L.ny + 2) * (L.nx + 2);
-  size_t smem = (n2 * 5 + (size_t)16 * (L.ny + 2)) * sizeof(double);
+  size_t smem = (n2 * 6 + (size_t)16 * (L.ny + 2)) * sizeof(double);
   const size_t smem_all = smem + (size_t)11 * L.nz * n2 * sizeof(double);
   const int all_smem = smem_all <= 226 * 1024 ? 1 : 0;
   if (all_smem) smem = smem_all;
