@@ -33,6 +33,8 @@ void launch_snapshot_x1(cudaStream_t st, const LevelView& L);
 void launch_relax_A(cudaStream_t st, const LevelView& L, const ColourSet& cs);
 void launch_relax_B(cudaStream_t st, const LevelView& L, const ColourSet& cs);
 void launch_relax_C(cudaStream_t st, const LevelView& L, const ColourSet& cs);
+// B and C fused, for neighbour-free levels with a chunked recurrence; reads the k=1 plane x1old, writes x1new completely
+void launch_relax_BC(cudaStream_t st, const LevelView& L, const ColourSet& cs, const double* x1old, double* x1new);
 // whole relax(lev, nsweeps) of a small, neighbour-free level in one single-CTA launch (red-black only)
 bool relax_small_supported(const LevelView& L);
 void launch_relax_small(cudaStream_t st, const LevelView& L, int nsweeps, int rank1);

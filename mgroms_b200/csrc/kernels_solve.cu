@@ -732,6 +732,81 @@ __global__ void __launch_bounds__(256) k_relax_C(LevelView L, ColourSet cs, int 
   store_mirrored(L.p, idx, v, j, i, L.ny, L.nx, (size_t)nz, (size_t)nz * ny2, cs.fuse_halo != 0);
   if (k == 0 && cs.fuse_halo) store_mirrored(L.x1, (size_t)j + (size_t)ny2 * i, v, j, i, L.ny, L.nx, 1, (size_t)ny2, true);
 }
+// Kernels B and C fused (neighbour-free levels): a CTA owns one chunk of rows (c0..c1) and a block of 2*TJ columns.
+// It first evaluates the chunked bottom recurrence on the trapezoid of the k=1 plane that its block depends on (warm-up
+// rows i0..c0-1 and E = c1-i0 extra columns on each side, so the values it commits are bit-identical to kernel B's),
+// entirely in shared memory, then streams p += s g over its rows with the Neumann mirrors.  The k=1 plane is double
+// buffered (x1old is read, x1new is written completely) because other CTAs still need the old values.
+// Saves the B launch and its serial latency on every colour.
+__global__ void __launch_bounds__(256) k_relax_BC(LevelView L, ColourSet cs, const double* __restrict__ x1old, double* __restrict__ x1new, int TJ) {
+  extern __shared__ __align__(16) double sm[];
+  const int nx = L.nx, ny = L.ny, ny2 = ny + 2, nz = L.nz;
+  const int c0 = 1 + blockIdx.y * L.rb_chunk, c1 = min(nx, c0 + L.rb_chunk - 1), i0 = max(1, c0 - L.rb_W);
+  const int E = c1 - i0;
+  const int jA = 2 * blockIdx.x * TJ + 1, jB = min(ny, jA + 2 * TJ - 1);
+  const int wlo = max(0, jA - 1 - E), whi = min(ny + 1, jB + 1 + E);
+  const int width = whi - wlo + 1, pitch = 2 * TJ + 2 * (L.rb_chunk + L.rb_W) + 4;
+  double* rowA = sm + 1; double* rowB = sm + pitch + 1;      // index [j - wlo], one pad cell on each side
+  double* sblk = sm + 2 * pitch;                             // [row - c0][j - jA]
+  for (int t = threadIdx.x; t < width; t += blockDim.x) rowA[t] = x1old[(size_t)(wlo + t) + (size_t)ny2 * (i0 - 1)];
+  if (threadIdx.x == 0) { rowA[-1] = 0.0; rowA[width] = 0.0; rowB[-1] = 0.0; rowB[width] = 0.0; }
+  double* prev = rowA; double* cur = rowB;
+  // this thread's entry of a step: the t-th column of the step's parity inside [max(1,wlo+1), min(ny,whi-1)]
+  const int lo = max(1, wlo + 1), hi = min(ny, whi - 1);
+  auto my_j = [&](int i) { const int js = 1 + ((i + cs.rb) & 1); int j = lo + (((lo ^ js) & 1) ? 1 : 0) + 2 * (int)threadIdx.x; return j; };
+  double o5 = 0, o8 = 0, oq = 0, og = 0;
+  { const int j = my_j(i0); if (j <= hi) { const size_t c = (size_t)j + (size_t)ny2 * i0; o5 = L.c5b[c]; o8 = L.c8b[c]; oq = L.q1[c]; og = L.g1[c]; } }
+  __syncthreads();
+  for (int i = i0; i <= c1; ++i) {
+    const int j = my_j(i);
+    const double a5 = o5, a8 = o8, aq = oq, ag = og;
+    if (i < c1) { const int jn = my_j(i + 1); if (jn <= hi) { const size_t c = (size_t)jn + (size_t)ny2 * (i + 1); o5 = L.c5b[c]; o8 = L.c8b[c]; oq = L.q1[c]; og = L.g1[c]; } }
+    if (j <= hi) {
+      const double sv = -(a5 * prev[j + 1 - wlo] + a8 * prev[j - 1 - wlo]);
+      cur[j - wlo] = aq + sv * ag;
+      if (i >= c0 && j >= jA && j <= jB) sblk[(i - c0) * 2 * TJ + (j - jA)] = sv;
+    }
+    if (threadIdx.x == 0) {
+      if (wlo == 0) cur[0] = x1old[(size_t)ny2 * i];
+      if (whi == ny + 1) cur[ny + 1 - wlo] = x1old[(size_t)(ny + 1) + (size_t)ny2 * i];
+    }
+    __syncthreads();
+    double* tmp = prev; prev = cur; cur = tmp;
+  }
+  // ---- C: stream the block's rows
+  const int nrows = c1 - c0 + 1, ncols = (jB - jA + 2) / 2;                 // colour columns per row in the block
+  const size_t sj = nz, si = (size_t)nz * ny2;
+  const int nelem = nrows * ncols * nz;
+#pragma unroll 4
+  for (int e = threadIdx.x; e < nelem; e += blockDim.x) {
+    const int k = e % nz; int t = e / nz; const int cj = t % ncols, r = t / ncols;
+    const int i = c0 + r;
+    const int js = 1 + ((i + cs.rb) & 1);
+    const int j = jA + (js - 1) + 2 * cj;
+    if (j > jB) continue;
+    const double sv = sblk[r * 2 * TJ + (j - jA)];
+    const size_t idx = IDX3(k, j, i, nz, ny2);
+    const double v = L.p[idx] + sv * L.g[idx];
+    store_mirrored(L.p, idx, v, j, i, ny, nx, sj, si, true);
+    if (k == 0) {
+      const size_t c2d = (size_t)j + (size_t)ny2 * i;
+      store_mirrored(x1new, c2d, v, j, i, ny, nx, 1, (size_t)ny2, true);
+      const int jp = (js == 1) ? j + 1 : j - 1;                               // the other-colour cell of the pair keeps its value
+      if (jp >= 1 && jp <= ny) store_mirrored(x1new, (size_t)jp + (size_t)ny2 * i, x1old[(size_t)jp + (size_t)ny2 * i], jp, i, ny, nx, 1, (size_t)ny2, true);
+    }
+  }
+}
+void launch_relax_BC(cudaStream_t st, const LevelView& L, const ColourSet& cs, const double* x1old, double* x1new) {
+  const int nyc = (L.ny + 1) / 2;
+  static int tj_env = 0;
+  if (!tj_env) { const char* e = getenv("MGB_BC_TJ"); tj_env = e ? atoi(e) : 8; }
+  int TJ = nyc < tj_env ? nyc : tj_env;
+  const int ntj = (nyc + TJ - 1) / TJ, nchunks = (L.nx + L.rb_chunk - 1) / L.rb_chunk;
+  const int pitch = 2 * TJ + 2 * (L.rb_chunk + L.rb_W) + 4;
+  const size_t smem = ((size_t)2 * pitch + (size_t)L.rb_chunk * 2 * TJ) * sizeof(double);
+  dim3 grid(ntj, nchunks);
+  k_relax_BC<<<grid, 256, smem, st>>>(L, cs, x1old, x1new, TJ); ++g_launches;
+}
 void launch_relax_C(cudaStream_t st, const LevelView& L, const ColourSet& cs) {
   const int nyc = (L.ny + 1) / 2;
   const int nvi = (L.nx - cs.istart) / cs.istep + 1;

@@ -43,6 +43,7 @@ struct LevelView {
   double *g;          // g = T^-1 e1 (rank-1 correction vector of the red-black bottom coupling)
   double *c5b, *c8b;  // 2-D copies of cA(5,1,:,:), cA(8,1,:,:) (bottom diagonal couplings)
   double *g1, *q1, *x1, *s;   // 2-D work planes of the rank-1 correction
+  double *x1b;                // second k=1 plane (double buffer of the fused B+C kernel)
   int rb_chunk, rb_W;         // the bottom recurrence runs in independent chunks of rb_chunk columns warmed up over rb_W columns
 };
 // warm-up length of the chunked bottom recurrence: smallest w with rho^w <= 1e-20 (rho = contraction factor)

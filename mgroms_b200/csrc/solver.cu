@@ -97,6 +97,7 @@ struct Solver {
   bool use_small = true;             // fused single-CTA relaxation on small neighbour-free levels
   bool use_graph = true;             // replay one captured F-cycle (+ residual) per outer iteration
   bool fuse_halo = true;             // neighbour-free levels: relax kernels write the Neumann halo themselves
+  bool fuse_bc = true;               // neighbour-free levels: kernels B and C fused
   cudaGraphExec_t cycle_graph = nullptr;
   long long cycle_graph_nodes = 0;
   int nlevs() const { return (int)L.size(); }
@@ -219,14 +220,20 @@ static int relax(int lev, int nsweeps) {
     }
     const bool rank1 = real_matrix && g.bottom_diag;
     const int fuse = (lonely && S.fuse_halo) ? 1 : 0;
-    if (fuse && rank1) launch_snapshot_x1(S.st, g.v);        // x1 = p(1,:,:) once; kernel C keeps it current afterwards
+    // B+C fused: chunked recurrence only, and only where the level is latency-bound (the separate C streams better on big levels)
+    const bool fuse_bc = fuse && rank1 && S.fuse_bc && g.v.rb_chunk < g.d.nx && g.n3() <= (size_t)3000000;
+    if (fuse && rank1) launch_snapshot_x1(S.st, g.v);        // x1 = p(1,:,:) once; the kernels keep it current afterwards
+    LevelView v = g.v;
     for (int it = 0; it < nsweeps; ++it)
       for (int rb = 1; rb <= 2; ++rb) {
         ColourSet cs{1, 1, 0, rb, 0, rank1 ? 1 : 0, fuse};
-        if (rank1 && !fuse) launch_snapshot_x1(S.st, g.v);
-        launch_relax_A(S.st, g.v, cs);
-        if (rank1) { launch_relax_B(S.st, g.v, cs); launch_relax_C(S.st, g.v, cs); }
-        if (!fuse) RC(fill_halo(lev, g.v.p, g.d.nz, 1));
+        if (rank1 && !fuse) launch_snapshot_x1(S.st, v);
+        launch_relax_A(S.st, v, cs);
+        if (rank1) {
+          if (fuse_bc) { launch_relax_BC(S.st, v, cs, v.x1, v.x1b); double* t = v.x1; v.x1 = v.x1b; v.x1b = t; }
+          else { launch_relax_B(S.st, v, cs); launch_relax_C(S.st, v, cs); }
+        }
+        if (!fuse) RC(fill_halo(lev, v.p, g.d.nz, 1));
       }
   } else if (m == "Four-Color" || m == "FC") {
     for (int it = 0; it < nsweeps; ++it)
@@ -567,7 +574,7 @@ static int init(int nx, int ny, int nz, int npx, int npy, int rank, const char* 
     RC(dalloc(&g.v.p, n3)); RC(dalloc(&g.v.b, n3)); RC(dalloc(&g.v.r, n3));
     for (int c = 0; c < 8; ++c) RC(dalloc(&g.v.cA[c], n3));
     RC(dalloc(&g.v.bet, n3)); RC(dalloc(&g.v.g, n3));
-    RC(dalloc(&g.v.c5b, n2)); RC(dalloc(&g.v.c8b, n2)); RC(dalloc(&g.v.g1, n2)); RC(dalloc(&g.v.q1, n2)); RC(dalloc(&g.v.x1, n2)); RC(dalloc(&g.v.s, n2));
+    RC(dalloc(&g.v.c5b, n2)); RC(dalloc(&g.v.c8b, n2)); RC(dalloc(&g.v.g1, n2)); RC(dalloc(&g.v.q1, n2)); RC(dalloc(&g.v.x1, n2)); RC(dalloc(&g.v.x1b, n2)); RC(dalloc(&g.v.s, n2));
     RC(dalloc(&g.dx, n2)); RC(dalloc(&g.dy, n2)); RC(dalloc(&g.zeta, n2)); RC(dalloc(&g.h, n2));
     RC(dalloc(&g.zr, (size_t)d.nz * (d.ny + 4) * (d.nx + 4))); RC(dalloc(&g.zw, (size_t)(d.nz + 1) * (d.ny + 4) * (d.nx + 4)));
     RC(dalloc(&g.cw, (size_t)(d.nz + 1) * n2));
@@ -601,6 +608,8 @@ static int init(int nx, int ny, int nz, int npx, int npy, int rank, const char* 
   S.use_small = !(ns && ns[0] == '1');
   const char* nf = std::getenv("MGB_NO_FUSED_HALO");
   S.fuse_halo = !(nf && nf[0] == '1');
+  const char* nb = std::getenv("MGB_NO_FUSED_BC");
+  S.fuse_bc = !(nb && nb[0] == '1');
   const char* ng = std::getenv("MGB_NO_GRAPH");
   S.use_graph = !(ng && ng[0] == '1');
   kernels_init();
@@ -824,22 +833,13 @@ int mgb_profile_level1(int reps, double* out4) {
   Level& g = S.L[0]; Level& c = S.L[1];
   cudaEvent_t a, b; CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
   float ms = 0;
-  const bool rank1 = (S.P.cmatrix == "real") && g.bottom_diag;
-  // relax: one colour = snapshot + A + B + C + halo
+  // relax: `reps` full red-black sweeps at level 1 through the production path; reported per colour half-sweep
   for (int pass = 0; pass < 2; ++pass) {
-    const int n = pass == 0 ? 2 : reps;
+    const int n = pass == 0 ? 1 : reps;
     CU(cudaEventRecord(a, S.st));
-    for (int r = 0; r < n; ++r) {
-      bool alone = true; for (int q = 0; q < 8; ++q) alone &= g.d.neighb[q] < 0;
-      const int fuse = (alone && S.fuse_halo) ? 1 : 0;
-      ColourSet cs{1, 1, 0, 1 + (r & 1), 0, rank1 ? 1 : 0, fuse};
-      if (rank1 && (!fuse || r == 0)) launch_snapshot_x1(S.st, g.v);
-      launch_relax_A(S.st, g.v, cs);
-      if (rank1) { launch_relax_B(S.st, g.v, cs); launch_relax_C(S.st, g.v, cs); }
-      if (!fuse) RC(fill_halo(1, g.v.p, g.d.nz, 1));
-    }
+    RC(relax(1, n));
     CU(cudaEventRecord(b, S.st)); CU(cudaEventSynchronize(b)); CU(cudaEventElapsedTime(&ms, a, b));
-    out4[0] = ms / n;
+    out4[0] = ms / (2 * n);
   }
   for (int pass = 0; pass < 2; ++pass) {
     const int n = pass == 0 ? 2 : reps;
