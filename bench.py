@@ -34,6 +34,7 @@ KIND = "seamount"
 TOL = 1e-10
 PROC_GRID = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (4, 2)}     # src/mg_grids.f90:593-594 rank <-> (pi,pj)
 BYTES_PER_POINT = dict(relax_colour=68, residual=88, restrict=10, prolong=17)
+BYTES_RANK1_PASS = 12    # extra bytes/pt of the exact-ordering correction pass p += s g (read q and g, write p on half the points)
 
 
 def measured_peaks():
@@ -255,9 +256,13 @@ def main():
             traffic = json.load(f).get("relax_colour_bytes_per_launch")
     except Exception:
         pass
+    ach80 = (BYTES_PER_POINT["relax_colour"] + BYTES_RANK1_PASS) * npts / (prof["relax_colour_ms"] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                "peak_source": peak_kind, "kernel": "relax colour half-sweep, level 1 (k_snapshot_x1 + k_relax_A + k_relax_B + k_relax_C + k_halo1_phys)",
+                "peak_source": peak_kind, "kernel": "relax colour half-sweep, level 1 (k_relax_A4 + k_relax_B + k_relax_C; halo and bottom-plane upkeep fused in)",
                 "algorithmic_bytes_per_launch": BYTES_PER_POINT["relax_colour"] * npts,
+                "achieved_counting_rank1_pass": ach80, "frac_counting_rank1_pass": ach80 / peak,
+                "note": "68 B/pt is SURVEY 8(d)'s figure for the colour; the exact reference sweep order needs a second pass p+=s*g (+12 B/pt), "
+                        "80 B/pt in total -- both fractions are given; k_relax_A4 alone runs at 4.5 TB/s (profiles/)",
                 "others_GBps": {k: BYTES_PER_POINT[k] * npts / (prof[k + "_ms"] * 1e-3) / 1e9 for k in ("residual", "restrict", "prolong")}}
 
     if rank == 0:

@@ -352,136 +352,19 @@ static void relax_tiling(const LevelView& L, const ColourSet& cs, int& TI, int& 
   ntj = (nyc + TJ - 1) / TJ; nti = (nvi + TI - 1) / TI;
   smem = (size_t)TI * TJ * (L.nz + 1) * 3 * sizeof(double);
 }
-// Kernel A, warp-autonomous variant: every WARP owns its own tile of TCW colour columns and runs the three phases
-// (k-parallel rhs -> per-column Thomas -> coalesced write-back) with __syncwarp only, so the warps of an SM are in
-// different phases at any time: no block barrier, no idle warps while one thread per column runs Thomas, and the
-// memory pipe always sees a number of warps with 27 loads per lane in flight.  Only rhs/x is staged in shared
-// memory ([TCW][nz+1] per warp); the Thomas thread reads its column's bet and cA(2) straight from global memory as
-// aligned double2 (each 128-byte line is consumed over 16 consecutive k, so it stays in L1).
-// Arithmetic is identical, operation by operation, to k_relax_A.
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 512 / (WARPS * 32)) k_relax_A3(LevelView L, ColourSet cs, int TI, int TJ, int ntj, int ntiles) {
-  extern __shared__ __align__(16) double sm[];
-  const int nz = L.nz, ny2 = L.ny + 2, pitch = nz + 1;
-  const int TC = TI * TJ;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x * WARPS + warp;
-  if (tile >= ntiles) return;
-  double* s_x = sm + (size_t)warp * TC * pitch;
-  const int tile_j = tile % ntj, tile_i = tile / ntj;
-  const int sj = nz; const size_t si = (size_t)nz * ny2;
-  const double* __restrict__ p = L.p; const double* __restrict__ b = L.b;
-  const double* __restrict__ c2 = L.cA[1]; const double* __restrict__ c3 = L.cA[2]; const double* __restrict__ c4 = L.cA[3];
-  const double* __restrict__ c5 = L.cA[4]; const double* __restrict__ c6 = L.cA[5]; const double* __restrict__ c7 = L.cA[6];
-  const double* __restrict__ c8 = L.cA[7]; const double* __restrict__ bet = L.bet;
-
-  // ---- phase 1: rhs, lanes along k
-  const int nelem = TC * nz;
-  for (int e = lane; e < nelem; e += 32) {
-    const int k = e % nz, c = e / nz;
-    const int ci = c / TJ, cj = c % TJ;
-    const int i = cs.istart + (tile_i * TI + ci) * cs.istep;
-    if (i > L.nx) continue;
-    const int j = colour_jstart(cs, i) + 2 * (tile_j * TJ + cj);
-    if (j > L.ny) continue;
-    const size_t idx = IDX3(k, j, i, nz, ny2);
-    const double bb = b[idx];
-    const double a3 = c3[idx],           q3 = p[idx - sj + 1];
-    const double a3n = c3[idx + sj - 1], q3n = p[idx + sj - 1];
-    const double a4 = c4[idx],           q4 = p[idx - sj];
-    const double a4n = c4[idx + sj],     q4n = p[idx + sj];
-    const double a5 = c5[idx],           q5 = p[idx - sj - 1];
-    const double a5n = c5[idx + sj + 1], q5n = p[idx + sj + 1];
-    const double a6 = c6[idx],           q6 = p[idx - si + 1];
-    const double a6n = c6[idx + si - 1], q6n = p[idx + si - 1];
-    const double a7 = c7[idx],           q7 = p[idx - si];
-    const double a7n = c7[idx + si],     q7n = p[idx + si];
-    const double a8 = c8[idx],           q8 = p[idx - si - 1];
-    const double a8n = c8[idx + si + 1], q8n = p[idx + si + 1];
-    const bool lo = (k > 0), hi = (k < nz - 1);
-    double acc = bb;
-    if (hi) acc = acc - a3 * q3;
-    if (lo) acc = acc - a3n * q3n;
-    acc = acc - a4 * q4;
-    acc = acc - a4n * q4n;
-    if (lo) acc = acc - a5 * q5;
-    if (hi) acc = acc - a5n * q5n;
-    if (hi) acc = acc - a6 * q6;
-    if (lo) acc = acc - a6n * q6n;
-    acc = acc - a7 * q7;
-    acc = acc - a7n * q7n;
-    if (lo) acc = acc - a8 * q8;
-    if (hi) acc = acc - a8n * q8n;
-    if (k == 0) {
-      if (cs.bottom_mode == 1) {
-        const size_t c2d = (size_t)j + (size_t)ny2 * i;
-        acc = acc - L.c5b[c2d - 1 + ny2] * L.x1[c2d - 1 + ny2];
-        acc = acc - L.c8b[c2d + 1 + ny2] * L.x1[c2d + 1 + ny2];
-      } else if (cs.bottom_mode == 2) {
-        acc = acc - a5 * p[idx + sj - si];
-        acc = acc - c5[idx - sj + si] * p[idx - sj + si];
-        acc = acc - a8 * p[idx - sj - si];
-        acc = acc - c8[idx + sj + si] * p[idx + sj + si];
-      }
-    }
-    s_x[c * pitch + k] = acc;
-  }
-  __syncwarp();
-
-  // ---- phase 2: Thomas, one lane per column; bet and cA(2) as double2 from global (k even -> 16-byte aligned)
-  for (int c = lane; c < TC; c += 32) {
-    const int ci = c / TJ, cj = c % TJ;
-    const int i = cs.istart + (tile_i * TI + ci) * cs.istep;
-    if (i > L.nx) continue;
-    const int j = colour_jstart(cs, i) + 2 * (tile_j * TJ + cj);
-    if (j > L.ny) continue;
-    const size_t idx0 = IDX3(0, j, i, nz, ny2);
-    const double2* __restrict__ bt2 = reinterpret_cast<const double2*>(bet + idx0);
-    const double2* __restrict__ cc2 = reinterpret_cast<const double2*>(c2 + idx0);   // cc2[m] = (cA2(k=2m), cA2(k=2m+1)), 0-based k
-    double* x = s_x + c * pitch;
-    // forward: x(k) = (rhs(k) - ud(k-1) x(k-1)) bet(k), ud(k-1) = cA2(k)
-    double xm = 0.0;
-#pragma unroll 4
-    for (int m = 0; m < nz / 2; ++m) {
-      const double2 bt = bt2[m], cc = cc2[m];
-      xm = (m == 0) ? x[0] * bt.x : (x[2 * m] - cc.x * xm) * bt.x;
-      x[2 * m] = xm;
-      xm = (x[2 * m + 1] - cc.y * xm) * bt.y;
-      x[2 * m + 1] = xm;
-    }
-    // backward: x(k) -= (ud(k) bet(k)) x(k+1), ud(k) = cA2(k+1)
-#pragma unroll 4
-    for (int m = nz / 2 - 1; m >= 0; --m) {
-      const double2 bt = bt2[m], cc = cc2[m];
-      if (m < nz / 2 - 1) { const double cnext = c2[idx0 + 2 * m + 2]; xm = x[2 * m + 1] - (cnext * bt.y) * xm; x[2 * m + 1] = xm; }
-      xm = x[2 * m] - (cc.y * bt.x) * xm;
-      x[2 * m] = xm;
-    }
-    if (cs.bottom_mode == 1) L.q1[(size_t)j + (size_t)ny2 * i] = xm;
-  }
-  __syncwarp();
-
-  // ---- phase 3: write back, lanes along k
-  double* __restrict__ pw = L.p;
-  for (int e = lane; e < nelem; e += 32) {
-    const int k = e % nz, c = e / nz;
-    const int ci = c / TJ, cj = c % TJ;
-    const int i = cs.istart + (tile_i * TI + ci) * cs.istep;
-    if (i > L.nx) continue;
-    const int j = colour_jstart(cs, i) + 2 * (tile_j * TJ + cj);
-    if (j > L.ny) continue;
-    pw[IDX3(k, j, i, nz, ny2)] = s_x[c * pitch + k];
-  }
-}
 // Kernel A, warp-specialised persistent variant.  A CTA of 8 warps loops over tiles with two shared-memory tile
 // buffers: warps 0..6 ("producers") run phase 1 (27 loads per lane in flight, rhs/bet/ud -> smem buffer) and the coalesced
 // write-back of the tile solved two steps earlier, warp 7 ("solver") only runs Thomas (one lane per column).  Named
 // barriers (bar.sync / bar.arrive) hand the buffers over, so producers never idle behind the serial Thomas phase and
 // the memory pipe is fed continuously.  Same arithmetic, operation by operation, as k_relax_A.
+// bulk prefetch of a contiguous global range into L2 (sm_90+): no registers, no shared memory, one instruction per range
+__device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(__cvta_generic_to_global(gptr)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-__global__ void __launch_bounds__(256, 2) k_relax_A4(LevelView L, ColourSet cs, int TI, int TJ, int ntj, int ntiles) {
+__global__ void __launch_bounds__(256, 2) k_relax_A4(LevelView L, ColourSet cs, int TI, int TJ, int ntj, int ntiles, int pf_dist) {
   extern __shared__ __align__(16) double sm[];
   const int nz = L.nz, ny2 = L.ny + 2, pitch = nz + 1;
   const int TC = TI * TJ;
@@ -584,6 +467,28 @@ __global__ void __launch_bounds__(256, 2) k_relax_A4(LevelView L, ColourSet cs, 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
       const int bsel = n & 1;
       double* s_rhs = sm + bsel * bufsz; const double* s_bet = s_rhs + (size_t)TC * pitch; const double* s_ud = s_bet + (size_t)TC * pitch;
+      if (pf_dist > 0) {                                    // stream the operands of a later tile of this CTA into L2
+        const int tp = tile + pf_dist * (int)gridDim.x;
+        if (tp < ntiles) {
+          const int tpj = tp % ntj, tpi = tp / ntj;
+          const unsigned seg = (unsigned)nz * 8u;
+          for (int c = lane; c < TC; c += 32) {
+            const int ci = c / TJ, cj = c % TJ;
+            const int i = cs.istart + (tpi * TI + ci) * cs.istep;
+            if (i > L.nx) continue;
+            const int j = colour_jstart(cs, i) + 2 * (tpj * TJ + cj);
+            if (j > L.ny) continue;
+            const size_t o = IDX3(0, j, i, nz, ny2);
+            l2_prefetch_bulk(L.b + o, seg); l2_prefetch_bulk(L.bet + o, seg);
+#pragma unroll
+            for (int a = 1; a < 8; ++a) l2_prefetch_bulk(L.cA[a] + o, seg);
+            l2_prefetch_bulk(L.cA[2] + o + sj, seg); l2_prefetch_bulk(L.cA[3] + o + sj, seg); l2_prefetch_bulk(L.cA[4] + o + sj, seg);
+            l2_prefetch_bulk(L.cA[5] + o + si, seg); l2_prefetch_bulk(L.cA[6] + o + si, seg); l2_prefetch_bulk(L.cA[7] + o + si, seg);
+            l2_prefetch_bulk(L.p + o + sj, seg); l2_prefetch_bulk(L.p + o - si, seg); l2_prefetch_bulk(L.p + o + si, seg);
+            if (cj == 0) l2_prefetch_bulk(L.p + o - sj, seg);
+          }
+        }
+      }
       named_bar_sync(1 + bsel, 256);                        // wait for the producers
       const int tile_j = tile % ntj, tile_i = tile / ntj;
       for (int c = lane; c < TC; c += 32) {
@@ -605,32 +510,17 @@ __global__ void __launch_bounds__(256, 2) k_relax_A4(LevelView L, ColourSet cs, 
     }
   }
 }
-static void relax_tiling3(const LevelView& L, const ColourSet& cs, int& TI, int& TJ, int& nti, int& ntj) {
-  const int nyc = (L.ny + 1) / 2;
-  const int nvi = (L.nx - cs.istart) / cs.istep + 1;
-  int tc = 2048 / L.nz; if (tc > 32) tc = 32; if (tc < 8) tc = 8;          // columns per warp tile
-  while (tc > 8 && ((size_t)nyc * nvi + tc - 1) / tc < 148 * 12) tc /= 2;   // small level: more, smaller tiles
-  TJ = nyc < tc ? nyc : tc;
-  TI = tc / TJ; if (TI < 1) TI = 1; if (TI > nvi) TI = nvi;
-  ntj = (nyc + TJ - 1) / TJ; nti = (nvi + TI - 1) / TI;
-}
 void launch_relax_A(cudaStream_t st, const LevelView& L, const ColourSet& cs) {
   static int variant = -1;
   if (variant < 0) { const char* e = getenv("MGB_RELAX_A"); variant = e ? atoi(e) : 4; }
-  if (variant == 3) {
-    int TI, TJ, nti, ntj;
-    relax_tiling3(L, cs, TI, TJ, nti, ntj);
-    const int ntiles = nti * ntj;
-    const size_t smem = (size_t)4 * TI * TJ * (L.nz + 1) * sizeof(double);
-    k_relax_A3<4><<<(ntiles + 3) / 4, 128, smem, st>>>(L, cs, TI, TJ, ntj, ntiles); ++g_launches;
-    return;
-  }
   if (variant == 4) {
     int TI, TJ, nti, ntj; size_t smem1;
     relax_tiling(L, cs, TI, TJ, nti, ntj, smem1);
     const int ntiles = nti * ntj;
     int grid = ntiles < 296 ? ntiles : 296;
-    k_relax_A4<<<grid, 256, 2 * smem1, st>>>(L, cs, TI, TJ, ntj, ntiles); ++g_launches;
+    static int pf = -1;
+    if (pf < 0) { const char* e = getenv("MGB_PF_DIST"); pf = e ? atoi(e) : 0; }
+    k_relax_A4<<<grid, 256, 2 * smem1, st>>>(L, cs, TI, TJ, ntj, ntiles, pf); ++g_launches;
     return;
   }
   int TI, TJ, nti, ntj; size_t smem;
@@ -729,8 +619,14 @@ __global__ void __launch_bounds__(256) k_relax_C(LevelView L, ColourSet cs, int 
   const double sv = L.s[(size_t)j + (size_t)ny2 * i];
   const size_t idx = IDX3(k, j, i, nz, ny2);
   const double v = L.p[idx] + sv * L.g[idx];
-  store_mirrored(L.p, idx, v, j, i, L.ny, L.nx, (size_t)nz, (size_t)nz * ny2, cs.fuse_halo != 0);
-  if (k == 0 && cs.fuse_halo) store_mirrored(L.x1, (size_t)j + (size_t)ny2 * i, v, j, i, L.ny, L.nx, 1, (size_t)ny2, true);
+  const bool edge = cs.fuse_halo && (i == 1 || i == L.nx || j <= 2 || j >= L.ny - 1);
+  if (!edge) {
+    L.p[idx] = v;
+    if (k == 0 && cs.fuse_halo) L.x1[(size_t)j + (size_t)ny2 * i] = v;
+  } else {
+    store_mirrored(L.p, idx, v, j, i, L.ny, L.nx, (size_t)nz, (size_t)nz * ny2, true);
+    if (k == 0) store_mirrored(L.x1, (size_t)j + (size_t)ny2 * i, v, j, i, L.ny, L.nx, 1, (size_t)ny2, true);
+  }
 }
 // Kernels B and C fused (neighbour-free levels): a CTA owns one chunk of rows (c0..c1) and a block of 2*TJ columns.
 // It first evaluates the chunked bottom recurrence on the trapezoid of the k=1 plane that its block depends on (warm-up
@@ -952,7 +848,6 @@ __global__ void __launch_bounds__(1024) k_relax_small(LevelView L, int nsweeps, 
 }
 void kernels_init() {
   cudaFuncSetAttribute(k_relax_A, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(k_relax_A3<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_relax_A4, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_relax_B<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   cudaFuncSetAttribute(k_relax_B<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
@@ -1002,11 +897,11 @@ __device__ __forceinline__ double block_sum_256(double v, double* s_red) {
 }
 
 // one block handles a chunk of one i-slab: elements (k, j) flattened, j = 1..ny
-__global__ void __launch_bounds__(256, 3) k_residual(LevelView L, int real_matrix, int chunks_per_i, double* __restrict__ partials) {
+__global__ void __launch_bounds__(256, 3) k_residual(LevelView L, int real_matrix, int chunks_per_i, double* __restrict__ partials, int probe) {
   __shared__ double s_red[8];
   const int nz = L.nz, ny = L.ny, ny2 = ny + 2;
   const int i = 1 + blockIdx.x / chunks_per_i, chunk = blockIdx.x % chunks_per_i;
-  const int sj = nz; const size_t si = (size_t)nz * ny2;
+  const int sj = probe ? 0 : nz; const size_t si = probe ? 0 : (size_t)nz * ny2; const int o1 = probe ? 0 : 1;
   const double* __restrict__ p = L.p; const double* __restrict__ b = L.b;
   const double* __restrict__ c1 = L.cA[0]; const double* __restrict__ c2 = L.cA[1]; const double* __restrict__ c3 = L.cA[2];
   const double* __restrict__ c4 = L.cA[3]; const double* __restrict__ c5 = L.cA[4]; const double* __restrict__ c6 = L.cA[5];
@@ -1021,20 +916,20 @@ __global__ void __launch_bounds__(256, 3) k_residual(LevelView L, int real_matri
     const size_t idx = IDX3(k, j, i, nz, ny2);
     const double bb = b[idx];
     const double a1 = c1[idx],           q1v = p[idx];
-    const double a2 = c2[idx],           q2 = p[idx - 1];
-    const double a2n = c2[idx + 1],      q2n = p[idx + 1];
-    const double a3 = c3[idx],           q3 = p[idx - sj + 1];
-    const double a3n = c3[idx + sj - 1], q3n = p[idx + sj - 1];
+    const double a2 = c2[idx],           q2 = p[idx - o1];
+    const double a2n = c2[idx + o1],      q2n = p[idx + o1];
+    const double a3 = c3[idx],           q3 = p[idx - sj + o1];
+    const double a3n = c3[idx + sj - o1], q3n = p[idx + sj - o1];
     const double a4 = c4[idx],           q4 = p[idx - sj];
     const double a4n = c4[idx + sj],     q4n = p[idx + sj];
-    const double a5 = c5[idx],           q5 = p[idx - sj - 1];
-    const double a5n = c5[idx + sj + 1], q5n = p[idx + sj + 1];
-    const double a6 = c6[idx],           q6 = p[idx - si + 1];
-    const double a6n = c6[idx + si - 1], q6n = p[idx + si - 1];
+    const double a5 = c5[idx],           q5 = p[idx - sj - o1];
+    const double a5n = c5[idx + sj + o1], q5n = p[idx + sj + o1];
+    const double a6 = c6[idx],           q6 = p[idx - si + o1];
+    const double a6n = c6[idx + si - o1], q6n = p[idx + si - o1];
     const double a7 = c7[idx],           q7 = p[idx - si];
     const double a7n = c7[idx + si],     q7n = p[idx + si];
-    const double a8 = c8[idx],           q8 = p[idx - si - 1];
-    const double a8n = c8[idx + si + 1], q8n = p[idx + si + 1];
+    const double a8 = c8[idx],           q8 = p[idx - si - o1];
+    const double a8n = c8[idx + si + o1], q8n = p[idx + si + o1];
     const bool lo = (k > 0), hi = (k < nz - 1);
     double acc = bb;
     acc = acc - a1 * q1v;
@@ -1074,13 +969,17 @@ __global__ void __launch_bounds__(256) k_reduce_final(const double* __restrict__
 }
 static int residual_chunks(const LevelView& L) {
   const int nelem = L.ny * L.nz;
-  int chunks = (nelem + 4095) / 4096;        // <= 16 elements per thread
+  static int per = 0;
+  if (!per) { const char* e = getenv("MGB_RES_CHUNK"); per = e ? atoi(e) : 4096; }
+  int chunks = (nelem + per - 1) / per;      // elements per CTA
   return chunks < 1 ? 1 : chunks;
 }
 int residual_num_partials(const LevelView& L) { return L.nx * residual_chunks(L); }
 void launch_residual(cudaStream_t st, const LevelView& L, int real_matrix, double* partials, double* sum_out) {
   const int chunks = residual_chunks(L);
-  k_residual<<<L.nx * chunks, 256, 0, st>>>(L, real_matrix, chunks, partials); ++g_launches;
+  static int probe = -1;
+  if (probe < 0) { const char* e = getenv("MGB_RES_PROBE"); probe = e ? atoi(e) : 0; }
+  k_residual<<<L.nx * chunks, 256, 0, st>>>(L, real_matrix, chunks, partials, probe); ++g_launches;
   k_reduce_final<<<1, 256, 0, st>>>(partials, L.nx * chunks, sum_out); ++g_launches;
 }
 __global__ void __launch_bounds__(256) k_sumsq(const double* __restrict__ a, int nz, int ny, int chunks_per_i, double* __restrict__ partials) {
