@@ -159,6 +159,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nsmall", type=int, default=0, help="namelist nsmall for N>1 (0 = default choice)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.gpus not in PROC_GRID:
@@ -183,7 +184,7 @@ def main():
     nh.reset_params()
     prm = dict(solver_prec=TOL, solver_maxiter=50)
     if world > 1:
-        prm["nsmall"] = 64      # gather the coarse levels onto one rank each (mg_gather) so they run latency-free of halo exchanges
+        prm["nsmall"] = args.nsmall or 64   # gather the coarse levels onto fewer ranks (mg_gather): no halo exchange on latency-bound levels
     nh.set_params(**prm)
     nh.nhydro_init(nx, ny, nz, npx, npy, rank, device=local)
     if world > 1:

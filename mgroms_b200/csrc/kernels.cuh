@@ -13,6 +13,9 @@ void kernels_init();           // one-time function attributes (dynamic shared m
 void launch_halo1_phys(cudaStream_t st, double* a, int nzl, int ny, int nx, Halo1Flags f);
 // corners that depend on just-received halos ("flag_*" logic, src/mg_mpi_exchange.f90:720-743)
 void launch_halo1_flagcorners(cudaStream_t st, double* a, int nzl, int ny, int nx, Halo1Flags f);
+// two-launch multi-GPU variant for nh = 1: `pre` = physical mirrors + pack of the S/N rows; `post` = unpack + flag corners (+ x1 upkeep)
+void launch_halo1_pre(cudaStream_t st, double* a, int nzl, int ny, int nx, Halo1Flags f, double* packS, double* packN);
+void launch_halo1_post(cudaStream_t st, double* a, int nzl, int ny, int nx, Halo1Flags f, const double* recvS, const double* recvN, double* x1);
 // nh = 2 array a(nzl, -1:ny+2, -1:nx+2) (zr, zw): ring 1 mirror, ring 2 = 2A-B, corners point mirror
 void launch_halo2_phys(cudaStream_t st, double* a, int nzl, int ny, int nx, Halo1Flags f);
 void launch_halo2_flagcorners(cudaStream_t st, double* a, int nzl, int ny, int nx, Halo1Flags f);
@@ -28,6 +31,7 @@ struct ColourSet {     // columns visited by one colour of a sweep
   int bottom_mode;     // 0: no k=1 diagonal terms ('simple');  1: rank-1 form (two (i+1) terms from the x1 snapshot);
                        // 2: all four terms read from p (no same-colour coupling, four-colour)
   int fuse_halo;       // 1: level without neighbour ranks -> the kernels write the Neumann halo themselves and keep x1 = p(1,:,:)
+                       // 2: level with neighbours -> kernel C keeps the interior of x1 current, the halo exchange does the ring
 };
 void launch_snapshot_x1(cudaStream_t st, const LevelView& L);
 void launch_relax_A(cudaStream_t st, const LevelView& L, const ColourSet& cs);

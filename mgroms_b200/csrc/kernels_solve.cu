@@ -111,6 +111,83 @@ void launch_halo1_flagcorners(cudaStream_t st, double* a, int nzl, int ny, int n
   k_halo1_flagcorners<<<blocks_for((size_t)4 * nzl, 128), 128, 0, st>>>(a, nzl, ny, nx, f); ++g_launches;
 }
 
+// Multi-GPU halo of an nh=1 field in two launches around the NCCL group:
+//   pre : physical-edge mirrors + physical corners (as k_halo1_phys) and packing of the strided S / N rows to send
+//   post: unpacking of the received S / N rows, the "flag" corners (taken from the received rows / columns) and, when
+//         x1 != nullptr, the upkeep of the persistent k=1 plane x1 = a(1,:,:) on the whole halo ring
+// E/W faces and corner columns are contiguous in the k-fastest layout and travel in place.
+__global__ void k_halo1_pre(double* __restrict__ a, int nzl, int ny, int nx, Halo1Flags f, double* __restrict__ packS, double* __restrict__ packN) {
+  const int ny2 = ny + 2;
+  const size_t n_ew = (size_t)ny * nzl, n_sn = (size_t)nx * nzl;
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < 2 * n_ew) {
+    int side = (int)(e / n_ew); size_t rem = e % n_ew;
+    if (side == 0 && !f.west) a[IDX3(0, 1, 0, nzl, ny2) + rem] = a[IDX3(0, 1, 1, nzl, ny2) + rem];
+    if (side == 1 && !f.east) a[IDX3(0, 1, nx + 1, nzl, ny2) + rem] = a[IDX3(0, 1, nx, nzl, ny2) + rem];
+    return;
+  }
+  e -= 2 * n_ew;
+  if (e < 2 * n_sn) {
+    int side = (int)(e / n_sn); size_t rem = e % n_sn;
+    int i = 1 + (int)(rem / nzl), k = (int)(rem % nzl);
+    if (side == 0) { const double v = a[IDX3(k, 1, i, nzl, ny2)]; if (f.south) packS[rem] = v; else a[IDX3(k, 0, i, nzl, ny2)] = v; }
+    else { const double v = a[IDX3(k, ny, i, nzl, ny2)]; if (f.north) packN[rem] = v; else a[IDX3(k, ny + 1, i, nzl, ny2)] = v; }
+    return;
+  }
+  e -= 2 * n_sn;
+  if (e < (size_t)4 * nzl) {
+    int c = (int)(e / nzl), k = (int)(e % nzl);
+    if (c == 0 && !f.sw && !f.south && !f.west) a[IDX3(k, 0, 0, nzl, ny2)] = a[IDX3(k, 1, 1, nzl, ny2)];
+    if (c == 1 && !f.se && !f.south && !f.east) a[IDX3(k, 0, nx + 1, nzl, ny2)] = a[IDX3(k, 1, nx, nzl, ny2)];
+    if (c == 2 && !f.ne && !f.north && !f.east) a[IDX3(k, ny + 1, nx + 1, nzl, ny2)] = a[IDX3(k, ny, nx, nzl, ny2)];
+    if (c == 3 && !f.nw && !f.north && !f.west) a[IDX3(k, ny + 1, 0, nzl, ny2)] = a[IDX3(k, ny, 1, nzl, ny2)];
+  }
+}
+__global__ void k_halo1_post(double* __restrict__ a, int nzl, int ny, int nx, Halo1Flags f, const double* __restrict__ recvS, const double* __restrict__ recvN,
+                             double* __restrict__ x1) {
+  const int ny2 = ny + 2;
+  const size_t n_sn = (size_t)nx * nzl;
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < 2 * n_sn) {                        // received S / N rows -> halo rows j = 0 / ny+1
+    int side = (int)(e / n_sn); size_t rem = e % n_sn;
+    int i = 1 + (int)(rem / nzl), k = (int)(rem % nzl);
+    if (side == 0) { if (f.south) a[IDX3(k, 0, i, nzl, ny2)] = recvS[rem]; if (x1 && k == 0) x1[(size_t)0 + (size_t)ny2 * i] = f.south ? recvS[rem] : a[IDX3(0, 0, i, nzl, ny2)]; }
+    else { if (f.north) a[IDX3(k, ny + 1, i, nzl, ny2)] = recvN[rem]; if (x1 && k == 0) x1[(size_t)(ny + 1) + (size_t)ny2 * i] = f.north ? recvN[rem] : a[IDX3(0, ny + 1, i, nzl, ny2)]; }
+    return;
+  }
+  e -= 2 * n_sn;
+  if (e < (size_t)4 * nzl) {                 // corners: received in place, or derived from a received row / column next to a wall
+    int c = (int)(e / nzl), k = (int)(e % nzl);
+    const size_t lastS = (size_t)k + (size_t)nzl * (nx - 1), firstS = (size_t)k;          // index into recvS / recvN for i = nx / i = 1
+    double v; size_t idx; size_t c2d;
+    if (c == 0) { idx = IDX3(k, 0, 0, nzl, ny2); c2d = 0;
+      if (!f.sw) { if (f.south) a[idx] = recvS[firstS]; else if (f.west) a[idx] = a[IDX3(k, 1, 0, nzl, ny2)]; } }
+    else if (c == 1) { idx = IDX3(k, 0, nx + 1, nzl, ny2); c2d = (size_t)ny2 * (nx + 1);
+      if (!f.se) { if (f.south) a[idx] = recvS[lastS]; else if (f.east) a[idx] = a[IDX3(k, 1, nx + 1, nzl, ny2)]; } }
+    else if (c == 2) { idx = IDX3(k, ny + 1, nx + 1, nzl, ny2); c2d = (size_t)(ny + 1) + (size_t)ny2 * (nx + 1);
+      if (!f.ne) { if (f.north) a[idx] = recvN[lastS]; else if (f.east) a[idx] = a[IDX3(k, ny, nx + 1, nzl, ny2)]; } }
+    else { idx = IDX3(k, ny + 1, 0, nzl, ny2); c2d = (size_t)(ny + 1);
+      if (!f.nw) { if (f.north) a[idx] = recvN[firstS]; else if (f.west) a[idx] = a[IDX3(k, ny, 0, nzl, ny2)]; } }
+    v = a[idx];
+    if (x1 && k == 0) x1[c2d] = v;
+    return;
+  }
+  e -= (size_t)4 * nzl;
+  if (x1 && e < (size_t)2 * ny) {            // E / W halo columns of the k=1 plane
+    int side = (int)(e / ny), j = 1 + (int)(e % ny);
+    const int i = side ? nx + 1 : 0;
+    x1[(size_t)j + (size_t)ny2 * i] = a[IDX3(0, j, i, nzl, ny2)];
+  }
+}
+void launch_halo1_pre(cudaStream_t st, double* a, int nzl, int ny, int nx, Halo1Flags f, double* packS, double* packN) {
+  size_t n = (size_t)2 * ny * nzl + (size_t)2 * nx * nzl + (size_t)4 * nzl;
+  k_halo1_pre<<<blocks_for(n, 256), 256, 0, st>>>(a, nzl, ny, nx, f, packS, packN); ++g_launches;
+}
+void launch_halo1_post(cudaStream_t st, double* a, int nzl, int ny, int nx, Halo1Flags f, const double* recvS, const double* recvN, double* x1) {
+  size_t n = (size_t)2 * nx * nzl + (size_t)4 * nzl + (size_t)2 * ny;
+  k_halo1_post<<<blocks_for(n, 256), 256, 0, st>>>(a, nzl, ny, nx, f, recvS, recvN, x1); ++g_launches;
+}
+
 // =====================================================================================================
 // halo, nh = 2 (zr, zw)   (reference: src/mg_mpi_exchange.f90:947-1101)
 // array a(nzl, -1:ny+2, -1:nx+2): index k + nzl*((j+1) + (ny+4)*(i+1))
@@ -333,7 +410,7 @@ __global__ void __launch_bounds__(256, 2) k_relax_A(LevelView L, ColourSet cs, i
     if (i > L.nx) continue;
     const int j = colour_jstart(cs, i) + 2 * (tile_j * TJ + cj);
     if (j > L.ny) continue;
-    store_mirrored(pw, IDX3(k, j, i, nz, ny2), s_rhs[c * pitch + k], j, i, L.ny, L.nx, sj, si, cs.fuse_halo && cs.bottom_mode != 1);
+    store_mirrored(pw, IDX3(k, j, i, nz, ny2), s_rhs[c * pitch + k], j, i, L.ny, L.nx, sj, si, cs.fuse_halo == 1 && cs.bottom_mode != 1);
   }
 }
 
@@ -389,7 +466,7 @@ __global__ void __launch_bounds__(256, 2) k_relax_A4(LevelView L, ColourSet cs, 
         if (i > L.nx) continue;
         const int j = colour_jstart(cs, i) + 2 * (t_j * TJ + cj);
         if (j > L.ny) continue;
-        store_mirrored(pw, IDX3(k, j, i, nz, ny2), s_x[c * pitch + k], j, i, L.ny, L.nx, sj, si, cs.fuse_halo && cs.bottom_mode != 1);
+        store_mirrored(pw, IDX3(k, j, i, nz, ny2), s_x[c * pitch + k], j, i, L.ny, L.nx, sj, si, cs.fuse_halo == 1 && cs.bottom_mode != 1);
       }
     };
     int n = 0;
@@ -619,10 +696,10 @@ __global__ void __launch_bounds__(256) k_relax_C(LevelView L, ColourSet cs, int 
   const double sv = L.s[(size_t)j + (size_t)ny2 * i];
   const size_t idx = IDX3(k, j, i, nz, ny2);
   const double v = L.p[idx] + sv * L.g[idx];
-  const bool edge = cs.fuse_halo && (i == 1 || i == L.nx || j <= 2 || j >= L.ny - 1);
+  const bool edge = (cs.fuse_halo == 1) && (i == 1 || i == L.nx || j <= 2 || j >= L.ny - 1);
   if (!edge) {
     L.p[idx] = v;
-    if (k == 0 && cs.fuse_halo) L.x1[(size_t)j + (size_t)ny2 * i] = v;
+    if (k == 0 && cs.fuse_halo) L.x1[(size_t)j + (size_t)ny2 * i] = v;   // fuse_halo == 2: keep x1 current, halo done by the exchange
   } else {
     store_mirrored(L.p, idx, v, j, i, L.ny, L.nx, (size_t)nz, (size_t)nz * ny2, true);
     if (k == 0) store_mirrored(L.x1, (size_t)j + (size_t)ny2 * i, v, j, i, L.ny, L.nx, 1, (size_t)ny2, true);
@@ -727,12 +804,14 @@ __global__ void __launch_bounds__(1024) k_relax_small(LevelView L, int nsweeps, 
   const double* b = L.b;
   const double *c2 = L.cA[1], *c3 = L.cA[2], *c4 = L.cA[3], *c5 = L.cA[4], *c6 = L.cA[5], *c7 = L.cA[6], *c8 = L.cA[7], *bet = L.bet, *g = L.g;
   const int n3 = NZ * n2;
-  if (all_smem) {
+  if (all_smem) {        // 1: p, cA2..8, bet staged (b and g stay in L2) ; 2: b and g as well
     double* base = rows + 16 * ny2;
-    const double* src[11] = {L.p, L.b, L.cA[1], L.cA[2], L.cA[3], L.cA[4], L.cA[5], L.cA[6], L.cA[7], L.bet, L.g};
-    for (int a = 0; a < 11; ++a) for (int e = threadIdx.x; e < n3; e += blockDim.x) base[a * n3 + e] = src[a][e];
-    p = base; b = base + n3; c2 = base + 2 * n3; c3 = base + 3 * n3; c4 = base + 4 * n3; c5 = base + 5 * n3; c6 = base + 6 * n3;
-    c7 = base + 7 * n3; c8 = base + 8 * n3; bet = base + 9 * n3; g = base + 10 * n3;
+    const double* src[11] = {L.p, L.cA[1], L.cA[2], L.cA[3], L.cA[4], L.cA[5], L.cA[6], L.cA[7], L.bet, L.b, L.g};
+    const int na = all_smem == 2 ? 11 : 9;
+    for (int a = 0; a < na; ++a) for (int e = threadIdx.x; e < n3; e += blockDim.x) base[a * n3 + e] = src[a][e];
+    p = base; c2 = base + n3; c3 = base + 2 * n3; c4 = base + 3 * n3; c5 = base + 4 * n3; c6 = base + 5 * n3; c7 = base + 6 * n3;
+    c8 = base + 7 * n3; bet = base + 8 * n3;
+    if (all_smem == 2) { b = base + 9 * n3; g = base + 10 * n3; }
   }
   if (rank1) for (int e = threadIdx.x; e < n2; e += blockDim.x) { c5b[e] = L.c5b[e]; c8b[e] = L.c8b[e]; g1[e] = L.g1[e]; }
   __syncthreads();
@@ -861,14 +940,15 @@ void kernels_init() {
 bool relax_small_supported(const LevelView& L) {
   const size_t n2 = (size_t)(L.ny + 2) * (L.nx + 2);
   const bool nz_ok = (L.nz == 2 || L.nz == 4 || L.nz == 8 || L.nz == 16);
-  return nz_ok && (L.ny % 2 == 0) && n2 <= (size_t)34 * 34;
+  // single-CTA relaxation pays off on tiny levels only; a 2-level (nz = 2) grid may be a little wider (coarsest level of a multi-GPU job)
+  return nz_ok && (L.ny % 2 == 0) && (n2 <= (size_t)34 * 34 || (L.nz == 2 && n2 <= (size_t)66 * 34));
 }
 void launch_relax_small(cudaStream_t st, const LevelView& L, int nsweeps, int rank1) {
   const size_t n2 = (size_t)(L.ny + 2) * (L.nx + 2);
   size_t smem = (n2 * 6 + (size_t)16 * (L.ny + 2)) * sizeof(double);
-  const size_t smem_all = smem + (size_t)11 * L.nz * n2 * sizeof(double);
-  const int all_smem = smem_all <= 226 * 1024 ? 1 : 0;
-  if (all_smem) smem = smem_all;
+  const size_t smem11 = smem + (size_t)11 * L.nz * n2 * sizeof(double), smem9 = smem + (size_t)9 * L.nz * n2 * sizeof(double);
+  const int all_smem = smem11 <= 226 * 1024 ? 2 : (smem9 <= 226 * 1024 ? 1 : 0);
+  if (all_smem == 2) smem = smem11; else if (all_smem == 1) smem = smem9;
   int threads = 64; const int ncol = L.nx * (L.ny / 2);
   while (threads < ncol && threads < 1024) threads *= 2;
   switch (L.nz) {

@@ -168,8 +168,33 @@ static int exchange(Level& g, double* a, int nzl, int nh) {
   return 0;
 }
 
-static int fill_halo(int lev, double* a, int nzl, int nh) {
+// nh = 1 with neighbours: pre kernel, one NCCL group, post kernel
+static int fill_halo1_multi(Level& g, double* a, int nzl, double* x1) {
+  const int nx = g.d.nx, ny = g.d.ny;
+  auto at = [&](int j, int i) { return a + (size_t)nzl * ((size_t)j + (size_t)(ny + 2) * (size_t)i); };
+  launch_halo1_pre(S.st, a, nzl, ny, nx, g.hf, g.pack8[0], g.pack8[2]);
+  NC(g_nccl.GroupStart());
+  const int* nb = g.d.neighb;
+  const size_t row = (size_t)nzl * nx, col = (size_t)nzl * ny, cor = (size_t)nzl;
+  if (nb[0] >= 0) { NC(g_nccl.Send(g.pack8[0], row, ncclDouble, nb[0], S.comm, S.st)); NC(g_nccl.Recv(g.unp8[0], row, ncclDouble, nb[0], S.comm, S.st)); }
+  if (nb[1] >= 0) { NC(g_nccl.Send(at(1, nx), col, ncclDouble, nb[1], S.comm, S.st)); NC(g_nccl.Recv(at(1, nx + 1), col, ncclDouble, nb[1], S.comm, S.st)); }
+  if (nb[2] >= 0) { NC(g_nccl.Send(g.pack8[2], row, ncclDouble, nb[2], S.comm, S.st)); NC(g_nccl.Recv(g.unp8[2], row, ncclDouble, nb[2], S.comm, S.st)); }
+  if (nb[3] >= 0) { NC(g_nccl.Send(at(1, 1), col, ncclDouble, nb[3], S.comm, S.st)); NC(g_nccl.Recv(at(1, 0), col, ncclDouble, nb[3], S.comm, S.st)); }
+  if (nb[4] >= 0) { NC(g_nccl.Send(at(1, 1), cor, ncclDouble, nb[4], S.comm, S.st)); NC(g_nccl.Recv(at(0, 0), cor, ncclDouble, nb[4], S.comm, S.st)); }
+  if (nb[5] >= 0) { NC(g_nccl.Send(at(1, nx), cor, ncclDouble, nb[5], S.comm, S.st)); NC(g_nccl.Recv(at(0, nx + 1), cor, ncclDouble, nb[5], S.comm, S.st)); }
+  if (nb[6] >= 0) { NC(g_nccl.Send(at(ny, nx), cor, ncclDouble, nb[6], S.comm, S.st)); NC(g_nccl.Recv(at(ny + 1, nx + 1), cor, ncclDouble, nb[6], S.comm, S.st)); }
+  if (nb[7] >= 0) { NC(g_nccl.Send(at(ny, 1), cor, ncclDouble, nb[7], S.comm, S.st)); NC(g_nccl.Recv(at(ny + 1, 0), cor, ncclDouble, nb[7], S.comm, S.st)); }
+  NC(g_nccl.GroupEnd());
+  launch_halo1_post(S.st, a, nzl, ny, nx, g.hf, g.unp8[0], g.unp8[2], x1);
+  return 0;
+}
+
+static int fill_halo(int lev, double* a, int nzl, int nh, double* x1 = nullptr) {
   Level& g = S.L[lev - 1];
+  if (nh == 1 && S.comm) {
+    bool any1 = false; for (int q = 0; q < 8; ++q) any1 |= g.d.neighb[q] >= 0;
+    if (any1) return fill_halo1_multi(g, a, nzl, x1);
+  }
   if (nh == 1) launch_halo1_phys(S.st, a, nzl, g.d.ny, g.d.nx, g.hf); else launch_halo2_phys(S.st, a, nzl, g.d.ny, g.d.nx, g.hf);
   bool any = false; for (int q = 0; q < 8; ++q) any |= g.d.neighb[q] >= 0;
   if (any) {
@@ -222,18 +247,18 @@ static int relax(int lev, int nsweeps) {
     const int fuse = (lonely && S.fuse_halo) ? 1 : 0;
     // B+C fused: chunked recurrence only, and only where the level is latency-bound (the separate C streams better on big levels)
     const bool fuse_bc = fuse && rank1 && S.fuse_bc && g.v.rb_chunk < g.d.nx && g.n3() <= (size_t)3000000;
-    if (fuse && rank1) launch_snapshot_x1(S.st, g.v);        // x1 = p(1,:,:) once; the kernels keep it current afterwards
+    const int xmode = fuse ? 1 : 2;                           // 2: neighbours -> C keeps x1's interior, the exchange its halo ring
+    if (rank1) launch_snapshot_x1(S.st, g.v);                 // x1 = p(1,:,:) once per call; kept current afterwards
     LevelView v = g.v;
     for (int it = 0; it < nsweeps; ++it)
       for (int rb = 1; rb <= 2; ++rb) {
-        ColourSet cs{1, 1, 0, rb, 0, rank1 ? 1 : 0, fuse};
-        if (rank1 && !fuse) launch_snapshot_x1(S.st, v);
+        ColourSet cs{1, 1, 0, rb, 0, rank1 ? 1 : 0, rank1 ? xmode : fuse};
         launch_relax_A(S.st, v, cs);
         if (rank1) {
           if (fuse_bc) { launch_relax_BC(S.st, v, cs, v.x1, v.x1b); double* t = v.x1; v.x1 = v.x1b; v.x1b = t; }
           else { launch_relax_B(S.st, v, cs); launch_relax_C(S.st, v, cs); }
         }
-        if (!fuse) RC(fill_halo(lev, v.p, g.d.nz, 1));
+        if (!fuse) RC(fill_halo(lev, v.p, g.d.nz, 1, rank1 ? v.x1 : nullptr));
       }
   } else if (m == "Four-Color" || m == "FC") {
     for (int it = 0; it < nsweeps; ++it)
