@@ -184,7 +184,7 @@ def main():
     nh.reset_params()
     prm = dict(solver_prec=TOL, solver_maxiter=50)
     if world > 1:
-        prm["nsmall"] = args.nsmall or 64   # gather the coarse levels onto fewer ranks (mg_gather): no halo exchange on latency-bound levels
+        prm["nsmall"] = args.nsmall or 256  # gather the coarse levels onto fewer ranks (mg_gather): no halo exchange on latency-bound levels
     nh.set_params(**prm)
     nh.nhydro_init(nx, ny, nz, npx, npy, rank, device=local)
     if world > 1:

@@ -71,6 +71,7 @@ CFGS = [
     ("rndtopo", 16, 32, 16, 2, 1, dict(solver_prec=1e-10, solver_maxiter=20, nsmall=16), "random"),     # gathered coarse levels
     ("seamount", 16, 16, 16, 2, 2, dict(solver_prec=1e-10, solver_maxiter=20), "random"),
     ("cuc", 16, 32, 8, 2, 2, dict(solver_prec=1e-9, solver_maxiter=20, nsmall=16), "wminus1"),
+    ("seamount", 16, 32, 16, 4, 2, dict(solver_prec=1e-10, solver_maxiter=20, nsmall=16), "random"),   # C4-like: two gather stages on 8 GPUs
 ]
 
 

@@ -181,3 +181,46 @@ def test_errors_are_loud(nh):
         nh.relax(1, 1)                                 # GS is not built: must say so, not fall back
     with pytest.raises(nh.MgbError):
         nh.get_field("nope")
+
+
+def test_full_size_config2_against_oracle_and_properties(nh):
+    """BASELINE config[1] at full size (seamount 512x512x64, dx = 156.25 m): the oracle still runs it in seconds, so the
+    residual history and the final pressure are compared directly, plus size-independent properties of the operator."""
+    from oracle.pyoracle import lib
+    nx, ny, nz = 512, 512, 64
+    prm = dict(solver_prec=1e-10, solver_maxiter=20)
+    make_product(nh, "seamount", nx, ny, nz, bench_dx=True, **prm)
+    nh.compute_rhs(None, *velocities("wminus1", nx, ny, nz)); nh.solve_p()
+    hg, _ = nh.history()
+    assert hg[-1] <= 1e-10 and len(hg) <= 8 and np.all(np.diff(hg) < 0)
+    pg = nh.get_field("p")
+    lib().mgo_set_num_threads(1)
+    o = make_oracle("seamount", nx, ny, nz, bench_dx=True, relax_order=1, **prm)
+    o.compute_rhs(); o.solve_p()
+    ho, _ = o.history()
+    history_close(hg, ho, rtol=1e-10, floor=1e-16)   # the norms are 1.7e7-term sums: sequential (oracle) vs tree (GPU) order differ at 1e-11
+    assert relerr(pg, o.get("p")) < 1e-11
+    assert np.array_equal(nh.get_field("b")[1:-1, 1:-1], o.get("b")[1:-1, 1:-1])
+    # A.1 = 0 below the surface level, at full size
+    shp = pg.shape
+    nh.set_field("p", np.ones(shp)); nh.set_field("b", np.zeros(shp)); nh.compute_residual(1)
+    r = nh.get_field("r")[1:-1, 1:-1]
+    diag = np.abs(nh.get_field("bet")[1:-1, 1:-1]).min() ** -1
+    assert np.abs(r[:, :, :-1]).max() < 1e-11 * diag
+    # restriction of a constant = 8x, prolongation of a constant = 1 (1/2 at the top), at full size
+    rr = np.zeros(shp); rr[1:-1, 1:-1] = 1.0
+    nh.set_field("r", rr); nh.fine2coarse(1)
+    assert np.array_equal(nh.get_field("b", 2)[1:-1, 1:-1], np.full((256, 256, 32), 8.0))
+    nh.set_field("p", np.ones(nh.get_field("p", 2).shape), 2); nh.set_field("p", np.zeros(shp)); nh.coarse2fine(1)
+    pf = nh.get_field("p")
+    assert np.array_equal(pf[1:-1, 1:-1, :-1], np.ones((512, 512, 63))) and np.array_equal(pf[1:-1, 1:-1, -1], np.full((512, 512), 0.5))
+
+
+def test_random_topography_config3_block_converges(nh):
+    """One 512x512x64 block of the random-topography case (steep-slope cross terms): converges to 1e-10, monotone history,
+    and the level-1 rank-1 recurrence runs chunked (contraction factor well below 1)."""
+    nx, ny, nz = 512, 512, 64
+    make_product(nh, "rndtopo", nx, ny, nz, bench_dx=True, solver_prec=1e-10, solver_maxiter=30)
+    nh.compute_rhs(None, *velocities("wminus1", nx, ny, nz)); nh.solve_p()
+    hg, _ = nh.history()
+    assert hg[-1] <= 1e-10 and np.all(np.diff(hg) < 0), hg
