@@ -303,123 +303,10 @@ void launch_snapshot_x1(cudaStream_t st, const LevelView& L) {
 
 __device__ __forceinline__ int colour_jstart(const ColourSet& cs, int i) { return cs.jrule == 0 ? 1 + ((i + cs.rb) & 1) : cs.jfix; }
 
-// Kernel A: for every column of the colour build the right-hand side of the vertical tridiagonal system
-// (k-parallel, coalesced along k), solve it by Thomas (one thread per column out of shared memory), write p.
-//   tile = TI consecutive visited i  x  TJ consecutive colour-columns in j ; TC = TI*TJ columns per CTA
-//   dynamic smem: 3 arrays [TC][nz+1] : rhs/x, bet, ud
-// Thomas recurrences (src/mg_relax.f90:308-334) with the pivots' reciprocals `bet` precomputed at matrix time:
-//   x(1) = rhs(1)*bet(1) ; x(k) = (rhs(k) - ud(k-1)*x(k-1))*bet(k) ; back: x(k) -= (ud(k)*bet(k))*x(k+1)
-__global__ void __launch_bounds__(256, 2) k_relax_A(LevelView L, ColourSet cs, int TI, int TJ, int ntj) {
-  extern __shared__ double sm[];
-  const int nz = L.nz, ny2 = L.ny + 2, pitch = nz + 1;
-  const int TC = TI * TJ;
-  double* s_rhs = sm;
-  double* s_bet = sm + (size_t)TC * pitch;
-  double* s_ud = s_bet + (size_t)TC * pitch;
-  const int tile_j = blockIdx.x % ntj, tile_i = blockIdx.x / ntj;
-  const int sj = nz;                       // stride of j
-  const size_t si = (size_t)nz * ny2;      // stride of i
-  const double* __restrict__ p = L.p;
-  const double* __restrict__ b = L.b;
-  const double* __restrict__ c2 = L.cA[1]; const double* __restrict__ c3 = L.cA[2]; const double* __restrict__ c4 = L.cA[3];
-  const double* __restrict__ c5 = L.cA[4]; const double* __restrict__ c6 = L.cA[5]; const double* __restrict__ c7 = L.cA[6];
-  const double* __restrict__ c8 = L.cA[7]; const double* __restrict__ bet = L.bet;
-
-  // ---- phase 1: rhs, coalesced along k
-  const int nelem = TC * nz;
-  for (int e = threadIdx.x; e < nelem; e += blockDim.x) {
-    const int k = e % nz, c = e / nz;
-    const int ci = c / TJ, cj = c % TJ;
-    const int i = cs.istart + (tile_i * TI + ci) * cs.istep;
-    if (i > L.nx) continue;
-    const int j = colour_jstart(cs, i) + 2 * (tile_j * TJ + cj);
-    if (j > L.ny) continue;
-    const size_t idx = IDX3(k, j, i, nz, ny2);
-    // all operands are loaded up front and unconditionally (every address is inside the arrays: the k-1 / k+1
-    // neighbours of an end point fall into the adjacent column) so that ~27 loads per thread are in flight at
-    // once; the edge predicates only select which products enter the sum -- same terms, same order as before.
-    const double bb = b[idx], bt = bet[idx], udv = c2[idx + 1];
-    const double a3 = c3[idx],           q3 = p[idx - sj + 1];
-    const double a3n = c3[idx + sj - 1], q3n = p[idx + sj - 1];
-    const double a4 = c4[idx],           q4 = p[idx - sj];
-    const double a4n = c4[idx + sj],     q4n = p[idx + sj];
-    const double a5 = c5[idx],           q5 = p[idx - sj - 1];
-    const double a5n = c5[idx + sj + 1], q5n = p[idx + sj + 1];
-    const double a6 = c6[idx],           q6 = p[idx - si + 1];
-    const double a6n = c6[idx + si - 1], q6n = p[idx + si - 1];
-    const double a7 = c7[idx],           q7 = p[idx - si];
-    const double a7n = c7[idx + si],     q7n = p[idx + si];
-    const double a8 = c8[idx],           q8 = p[idx - si - 1];
-    const double a8n = c8[idx + si + 1], q8n = p[idx + si + 1];
-    const bool lo = (k > 0), hi = (k < nz - 1);
-    double acc = bb;
-    if (hi) acc = acc - a3 * q3;
-    if (lo) acc = acc - a3n * q3n;
-    acc = acc - a4 * q4;
-    acc = acc - a4n * q4n;
-    if (lo) acc = acc - a5 * q5;
-    if (hi) acc = acc - a5n * q5n;
-    if (hi) acc = acc - a6 * q6;
-    if (lo) acc = acc - a6n * q6n;
-    acc = acc - a7 * q7;
-    acc = acc - a7n * q7n;
-    if (lo) acc = acc - a8 * q8;
-    if (hi) acc = acc - a8n * q8n;
-    if (k == 0) {
-      if (cs.bottom_mode == 1) {          // rank-1 form: only the two not-yet-updated (i+1) neighbours, from the snapshot
-        const size_t c2d = (size_t)j + (size_t)ny2 * i;
-        acc = acc - L.c5b[c2d - 1 + ny2] * L.x1[c2d - 1 + ny2];
-        acc = acc - L.c8b[c2d + 1 + ny2] * L.x1[c2d + 1 + ny2];
-      } else if (cs.bottom_mode == 2) {   // all four bottom-diagonal terms from p (src/mg_relax.f90:271-276)
-        acc = acc - a5 * p[idx + sj - si];
-        acc = acc - c5[idx - sj + si] * p[idx - sj + si];
-        acc = acc - a8 * p[idx - sj - si];
-        acc = acc - c8[idx + sj + si] * p[idx + sj + si];
-      }
-    }
-    s_rhs[c * pitch + k] = acc;
-    s_bet[c * pitch + k] = bt;
-    s_ud[c * pitch + k] = hi ? udv : 0.0;
-  }
-  __syncthreads();
-
-  // ---- phase 2: Thomas, one thread per column
-  for (int c = threadIdx.x; c < TC; c += blockDim.x) {
-    const int ci = c / TJ, cj = c % TJ;
-    const int i = cs.istart + (tile_i * TI + ci) * cs.istep;
-    if (i > L.nx) continue;
-    const int j = colour_jstart(cs, i) + 2 * (tile_j * TJ + cj);
-    if (j > L.ny) continue;
-    double* x = s_rhs + c * pitch;
-    const double* bt = s_bet + c * pitch;
-    const double* ud = s_ud + c * pitch;
-    double xm = x[0] * bt[0];
-    x[0] = xm;
-    for (int k = 1; k < nz; ++k) { xm = (x[k] - ud[k - 1] * xm) * bt[k]; x[k] = xm; }
-    for (int k = nz - 2; k >= 0; --k) { xm = x[k] - (ud[k] * bt[k]) * xm; x[k] = xm; }
-    if (cs.bottom_mode == 1) L.q1[(size_t)j + (size_t)ny2 * i] = xm;
-  }
-  __syncthreads();
-
-  // ---- phase 3: write back, coalesced along k
-  double* __restrict__ pw = L.p;
-  for (int e = threadIdx.x; e < nelem; e += blockDim.x) {
-    const int k = e % nz, c = e / nz;
-    const int ci = c / TJ, cj = c % TJ;
-    const int i = cs.istart + (tile_i * TI + ci) * cs.istep;
-    if (i > L.nx) continue;
-    const int j = colour_jstart(cs, i) + 2 * (tile_j * TJ + cj);
-    if (j > L.ny) continue;
-    store_mirrored(pw, IDX3(k, j, i, nz, ny2), s_rhs[c * pitch + k], j, i, L.ny, L.nx, sj, si, cs.fuse_halo == 1 && cs.bottom_mode != 1);
-  }
-}
-
 static void relax_tiling(const LevelView& L, const ColourSet& cs, int& TI, int& TJ, int& nti, int& ntj, size_t& smem) {
   const int nyc = (L.ny + 1) / 2;                    // colour columns per visited i (upper bound)
   const int nvi = (L.nx - cs.istart) / cs.istep + 1; // visited i
-  static int tile_pts = 0;
-  if (!tile_pts) { const char* e = getenv("MGB_TILE_PTS"); tile_pts = e ? atoi(e) : 1024; }
-  int tc_max = tile_pts / L.nz;                      // columns per CTA: aim at ~2048 points per tile (8 per thread)
+  int tc_max = 1024 / L.nz;                          // columns per tile: ~1024 points (two 25 KB buffers per CTA leave most of the L1)
   if (tc_max < 16) tc_max = 16;
   if (tc_max > 1024) tc_max = 1024;
   while (tc_max > 1 && (size_t)tc_max * (L.nz + 1) * 3 * sizeof(double) > 100 * 1024) tc_max /= 2;
@@ -434,14 +321,10 @@ static void relax_tiling(const LevelView& L, const ColourSet& cs, int& TI, int& 
 // write-back of the tile solved two steps earlier, warp 7 ("solver") only runs Thomas (one lane per column).  Named
 // barriers (bar.sync / bar.arrive) hand the buffers over, so producers never idle behind the serial Thomas phase and
 // the memory pipe is fed continuously.  Same arithmetic, operation by operation, as k_relax_A.
-// bulk prefetch of a contiguous global range into L2 (sm_90+): no registers, no shared memory, one instruction per range
-__device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, unsigned bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(__cvta_generic_to_global(gptr)), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-__global__ void __launch_bounds__(256, 2) k_relax_A4(LevelView L, ColourSet cs, int TI, int TJ, int ntj, int ntiles, int pf_dist) {
+__global__ void __launch_bounds__(256, 2) k_relax_A4(LevelView L, ColourSet cs, int TI, int TJ, int ntj, int ntiles) {
   extern __shared__ __align__(16) double sm[];
   const int nz = L.nz, ny2 = L.ny + 2, pitch = nz + 1;
   const int TC = TI * TJ;
@@ -544,28 +427,6 @@ __global__ void __launch_bounds__(256, 2) k_relax_A4(LevelView L, ColourSet cs, 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
       const int bsel = n & 1;
       double* s_rhs = sm + bsel * bufsz; const double* s_bet = s_rhs + (size_t)TC * pitch; const double* s_ud = s_bet + (size_t)TC * pitch;
-      if (pf_dist > 0) {                                    // stream the operands of a later tile of this CTA into L2
-        const int tp = tile + pf_dist * (int)gridDim.x;
-        if (tp < ntiles) {
-          const int tpj = tp % ntj, tpi = tp / ntj;
-          const unsigned seg = (unsigned)nz * 8u;
-          for (int c = lane; c < TC; c += 32) {
-            const int ci = c / TJ, cj = c % TJ;
-            const int i = cs.istart + (tpi * TI + ci) * cs.istep;
-            if (i > L.nx) continue;
-            const int j = colour_jstart(cs, i) + 2 * (tpj * TJ + cj);
-            if (j > L.ny) continue;
-            const size_t o = IDX3(0, j, i, nz, ny2);
-            l2_prefetch_bulk(L.b + o, seg); l2_prefetch_bulk(L.bet + o, seg);
-#pragma unroll
-            for (int a = 1; a < 8; ++a) l2_prefetch_bulk(L.cA[a] + o, seg);
-            l2_prefetch_bulk(L.cA[2] + o + sj, seg); l2_prefetch_bulk(L.cA[3] + o + sj, seg); l2_prefetch_bulk(L.cA[4] + o + sj, seg);
-            l2_prefetch_bulk(L.cA[5] + o + si, seg); l2_prefetch_bulk(L.cA[6] + o + si, seg); l2_prefetch_bulk(L.cA[7] + o + si, seg);
-            l2_prefetch_bulk(L.p + o + sj, seg); l2_prefetch_bulk(L.p + o - si, seg); l2_prefetch_bulk(L.p + o + si, seg);
-            if (cj == 0) l2_prefetch_bulk(L.p + o - sj, seg);
-          }
-        }
-      }
       named_bar_sync(1 + bsel, 256);                        // wait for the producers
       const int tile_j = tile % ntj, tile_i = tile / ntj;
       for (int c = lane; c < TC; c += 32) {
@@ -588,23 +449,11 @@ __global__ void __launch_bounds__(256, 2) k_relax_A4(LevelView L, ColourSet cs, 
   }
 }
 void launch_relax_A(cudaStream_t st, const LevelView& L, const ColourSet& cs) {
-  static int variant = -1;
-  if (variant < 0) { const char* e = getenv("MGB_RELAX_A"); variant = e ? atoi(e) : 4; }
-  if (variant == 4) {
-    int TI, TJ, nti, ntj; size_t smem1;
-    relax_tiling(L, cs, TI, TJ, nti, ntj, smem1);
-    const int ntiles = nti * ntj;
-    int grid = ntiles < 296 ? ntiles : 296;
-    static int pf = -1;
-    if (pf < 0) { const char* e = getenv("MGB_PF_DIST"); pf = e ? atoi(e) : 0; }
-    k_relax_A4<<<grid, 256, 2 * smem1, st>>>(L, cs, TI, TJ, ntj, ntiles, pf); ++g_launches;
-    return;
-  }
-  int TI, TJ, nti, ntj; size_t smem;
-  relax_tiling(L, cs, TI, TJ, nti, ntj, smem);
-  static int nthr = 0;
-  if (!nthr) { const char* e = getenv("MGB_A_THREADS"); nthr = e ? atoi(e) : 256; }
-  k_relax_A<<<nti * ntj, nthr, smem, st>>>(L, cs, TI, TJ, ntj); ++g_launches;
+  int TI, TJ, nti, ntj; size_t smem1;
+  relax_tiling(L, cs, TI, TJ, nti, ntj, smem1);
+  const int ntiles = nti * ntj;
+  const int grid = ntiles < 296 ? ntiles : 296;        // persistent: two CTAs per SM
+  k_relax_A4<<<grid, 256, 2 * smem1, st>>>(L, cs, TI, TJ, ntj, ntiles); ++g_launches;
 }
 
 // Kernel B: the sequential part of the red-black bottom coupling, on the 2-D k=1 plane only.
@@ -771,9 +620,7 @@ __global__ void __launch_bounds__(256) k_relax_BC(LevelView L, ColourSet cs, con
 }
 void launch_relax_BC(cudaStream_t st, const LevelView& L, const ColourSet& cs, const double* x1old, double* x1new) {
   const int nyc = (L.ny + 1) / 2;
-  static int tj_env = 0;
-  if (!tj_env) { const char* e = getenv("MGB_BC_TJ"); tj_env = e ? atoi(e) : 8; }
-  int TJ = nyc < tj_env ? nyc : tj_env;
+  const int TJ = nyc < 8 ? nyc : 8;          // narrow blocks: many CTAs, the trapezoid overhead is 2-D only
   const int ntj = (nyc + TJ - 1) / TJ, nchunks = (L.nx + L.rb_chunk - 1) / L.rb_chunk;
   const int pitch = 2 * TJ + 2 * (L.rb_chunk + L.rb_W) + 4;
   const size_t smem = ((size_t)2 * pitch + (size_t)L.rb_chunk * 2 * TJ) * sizeof(double);
@@ -926,7 +773,6 @@ __global__ void __launch_bounds__(1024) k_relax_small(LevelView L, int nsweeps, 
   if (all_smem) for (int e = threadIdx.x; e < n3; e += blockDim.x) L.p[e] = p[e];
 }
 void kernels_init() {
-  cudaFuncSetAttribute(k_relax_A, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_relax_A4, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_relax_B<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   cudaFuncSetAttribute(k_relax_B<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
@@ -977,11 +823,11 @@ __device__ __forceinline__ double block_sum_256(double v, double* s_red) {
 }
 
 // one block handles a chunk of one i-slab: elements (k, j) flattened, j = 1..ny
-__global__ void __launch_bounds__(256, 3) k_residual(LevelView L, int real_matrix, int chunks_per_i, double* __restrict__ partials, int probe) {
+__global__ void __launch_bounds__(256, 3) k_residual(LevelView L, int real_matrix, int chunks_per_i, double* __restrict__ partials) {
   __shared__ double s_red[8];
   const int nz = L.nz, ny = L.ny, ny2 = ny + 2;
   const int i = 1 + blockIdx.x / chunks_per_i, chunk = blockIdx.x % chunks_per_i;
-  const int sj = probe ? 0 : nz; const size_t si = probe ? 0 : (size_t)nz * ny2; const int o1 = probe ? 0 : 1;
+  const int sj = nz; const size_t si = (size_t)nz * ny2;
   const double* __restrict__ p = L.p; const double* __restrict__ b = L.b;
   const double* __restrict__ c1 = L.cA[0]; const double* __restrict__ c2 = L.cA[1]; const double* __restrict__ c3 = L.cA[2];
   const double* __restrict__ c4 = L.cA[3]; const double* __restrict__ c5 = L.cA[4]; const double* __restrict__ c6 = L.cA[5];
@@ -996,20 +842,20 @@ __global__ void __launch_bounds__(256, 3) k_residual(LevelView L, int real_matri
     const size_t idx = IDX3(k, j, i, nz, ny2);
     const double bb = b[idx];
     const double a1 = c1[idx],           q1v = p[idx];
-    const double a2 = c2[idx],           q2 = p[idx - o1];
-    const double a2n = c2[idx + o1],      q2n = p[idx + o1];
-    const double a3 = c3[idx],           q3 = p[idx - sj + o1];
-    const double a3n = c3[idx + sj - o1], q3n = p[idx + sj - o1];
+    const double a2 = c2[idx],           q2 = p[idx - 1];
+    const double a2n = c2[idx + 1],      q2n = p[idx + 1];
+    const double a3 = c3[idx],           q3 = p[idx - sj + 1];
+    const double a3n = c3[idx + sj - 1], q3n = p[idx + sj - 1];
     const double a4 = c4[idx],           q4 = p[idx - sj];
     const double a4n = c4[idx + sj],     q4n = p[idx + sj];
-    const double a5 = c5[idx],           q5 = p[idx - sj - o1];
-    const double a5n = c5[idx + sj + o1], q5n = p[idx + sj + o1];
-    const double a6 = c6[idx],           q6 = p[idx - si + o1];
-    const double a6n = c6[idx + si - o1], q6n = p[idx + si - o1];
+    const double a5 = c5[idx],           q5 = p[idx - sj - 1];
+    const double a5n = c5[idx + sj + 1], q5n = p[idx + sj + 1];
+    const double a6 = c6[idx],           q6 = p[idx - si + 1];
+    const double a6n = c6[idx + si - 1], q6n = p[idx + si - 1];
     const double a7 = c7[idx],           q7 = p[idx - si];
     const double a7n = c7[idx + si],     q7n = p[idx + si];
-    const double a8 = c8[idx],           q8 = p[idx - si - o1];
-    const double a8n = c8[idx + si + o1], q8n = p[idx + si + o1];
+    const double a8 = c8[idx],           q8 = p[idx - si - 1];
+    const double a8n = c8[idx + si + 1], q8n = p[idx + si + 1];
     const bool lo = (k > 0), hi = (k < nz - 1);
     double acc = bb;
     acc = acc - a1 * q1v;
@@ -1049,17 +895,13 @@ __global__ void __launch_bounds__(256) k_reduce_final(const double* __restrict__
 }
 static int residual_chunks(const LevelView& L) {
   const int nelem = L.ny * L.nz;
-  static int per = 0;
-  if (!per) { const char* e = getenv("MGB_RES_CHUNK"); per = e ? atoi(e) : 4096; }
-  int chunks = (nelem + per - 1) / per;      // elements per CTA
+  int chunks = (nelem + 4095) / 4096;        // <= 16 elements per thread
   return chunks < 1 ? 1 : chunks;
 }
 int residual_num_partials(const LevelView& L) { return L.nx * residual_chunks(L); }
 void launch_residual(cudaStream_t st, const LevelView& L, int real_matrix, double* partials, double* sum_out) {
   const int chunks = residual_chunks(L);
-  static int probe = -1;
-  if (probe < 0) { const char* e = getenv("MGB_RES_PROBE"); probe = e ? atoi(e) : 0; }
-  k_residual<<<L.nx * chunks, 256, 0, st>>>(L, real_matrix, chunks, partials, probe); ++g_launches;
+  k_residual<<<L.nx * chunks, 256, 0, st>>>(L, real_matrix, chunks, partials); ++g_launches;
   k_reduce_final<<<1, 256, 0, st>>>(partials, L.nx * chunks, sum_out); ++g_launches;
 }
 __global__ void __launch_bounds__(256) k_sumsq(const double* __restrict__ a, int nz, int ny, int chunks_per_i, double* __restrict__ partials) {

@@ -124,6 +124,14 @@ static Halo1Flags flags_of(const LevelDims& d) {
   return f;
 }
 
+// end of an API call: wait for the stream and surface both execution errors and launch-configuration errors
+static int finish() {
+  cudaError_t e = cudaStreamSynchronize(S.st);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(std::string("CUDA failure: ") + cudaGetErrorString(e));
+  return 0;
+}
+
 static int check_level(int lev) {
   if (!S.inited) return fail("mgb_init has not been called");
   if (lev < 1 || lev > S.nlevs()) return fail("level out of range");
@@ -292,7 +300,7 @@ static int global_sum(int lev, const double* dev_local, double* out) {
   } else {
     CU(cudaMemcpyAsync(&v, dev_local, sizeof(double), cudaMemcpyDeviceToHost, S.st));
   }
-  CU(cudaStreamSynchronize(S.st));
+  RC(finish());
   const LevelDims& d = S.L[lev - 1].d; const LevelDims& d1 = S.L[0].d;
   *out = v * (d.npx * d.npy) / (d1.npx * d1.npy);
   return 0;
@@ -472,7 +480,7 @@ static int define_matrices() {
     g.v.rb_W = rb_warmup(rho);
     g.v.rb_chunk = (g.v.rb_W > RB_WMAX) ? g.d.nx : RB_CHUNK;
   }
-  CU(cudaStreamSynchronize(S.st));
+  RC(finish());
   S.have_matrices = true;
   return 0;
 }
@@ -502,8 +510,7 @@ static int download_uvw(double* u, double* v, double* w) {
   CU(cudaMemcpyAsync(v, S.stage, n_v() * sizeof(double), cudaMemcpyDeviceToHost, S.st));
   launch_transpose_kji_to_ijk(S.st, S.wt, S.stage, d.nx + 2, d.ny + 2, d.nz + 1);
   CU(cudaMemcpyAsync(w, S.stage, n_w() * sizeof(double), cudaMemcpyDeviceToHost, S.st));
-  CU(cudaStreamSynchronize(S.st));
-  return 0;
+  return finish();
 }
 
 // exchange of one flux face with the neighbour (what fill_halo(...,lbc_null) does where a neighbour exists):
@@ -757,8 +764,7 @@ int mgb_matrices(const double* dx, const double* dy, const double* zeta, const d
 int mgb_compute_rhs(const double* rmask, const double* u, const double* v, const double* w) {
   if (!S.have_matrices) return fail("mgb_matrices has not been called");
   RC(set_rmask(rmask)); RC(upload_uvw(u, v, w)); RC(compute_rhs_device());
-  CU(cudaStreamSynchronize(S.st));
-  return 0;
+  return finish();
 }
 int mgb_check_nondivergence(const double* rmask, const double* u, const double* v, const double* w) { return mgb_compute_rhs(rmask, u, v, w); }
 int mgb_solve_p(void) { if (!S.inited) return fail("mgb_init has not been called"); return solve_p(); }
@@ -789,15 +795,15 @@ int mgb_write_fort100(const char* path) {
 double mgb_last_solve_ms(void) { return S.last_ms; }
 int mgb_last_solve_iters(void) { return S.last_iters; }
 
-int mgb_relax(int lev, int nsweeps) { RC(check_level(lev)); RC(relax(lev, nsweeps)); CU(cudaStreamSynchronize(S.st)); return 0; }
+int mgb_relax(int lev, int nsweeps) { RC(check_level(lev)); RC(relax(lev, nsweeps)); return finish(); }
 int mgb_residual(int lev, double* res) {
   RC(check_level(lev)); RC(residual(lev));
   double s = 0; RC(global_sum(lev, S.sums, &s)); *res = std::sqrt(s); return 0;
 }
-int mgb_fine2coarse(int lev) { RC(check_level(lev)); if (lev >= S.nlevs()) return fail("no coarser level"); RC(fine2coarse(lev, false)); CU(cudaStreamSynchronize(S.st)); return 0; }
-int mgb_coarse2fine(int lev) { RC(check_level(lev)); if (lev >= S.nlevs()) return fail("no coarser level"); RC(coarse2fine(lev, false)); CU(cudaStreamSynchronize(S.st)); return 0; }
-int mgb_fcycle(void) { RC(check_level(1)); RC(fcycle()); CU(cudaStreamSynchronize(S.st)); return 0; }
-int mgb_vcycle(int lev1) { RC(check_level(lev1)); RC(vcycle(lev1)); CU(cudaStreamSynchronize(S.st)); return 0; }
+int mgb_fine2coarse(int lev) { RC(check_level(lev)); if (lev >= S.nlevs()) return fail("no coarser level"); RC(fine2coarse(lev, false)); return finish(); }
+int mgb_coarse2fine(int lev) { RC(check_level(lev)); if (lev >= S.nlevs()) return fail("no coarser level"); RC(coarse2fine(lev, false)); return finish(); }
+int mgb_fcycle(void) { RC(check_level(1)); RC(fcycle()); return finish(); }
+int mgb_vcycle(int lev1) { RC(check_level(lev1)); RC(vcycle(lev1)); return finish(); }
 int mgb_fill_halo(int lev, const char* name) {
   RC(check_level(lev)); FieldRef f; RC(field_ref(lev, name, f));
   if (f.is_cA) return fail("cA halo is only exchanged with bmask (not built)");
