@@ -985,7 +985,7 @@ __global__ void __launch_bounds__(256) k_prolong(const double* __restrict__ xc, 
 // thread per COARSE interior point: computes its 8 fine children from the 27 surrounding coarse values (each child with
 // exactly the expression of the reference, see k_prolong) and writes them as (k,k+1) double2 pairs: 27 cached loads
 // per 8 fine points instead of 64, and 16-byte coalesced read-modify-write of p.
-__global__ void __launch_bounds__(256) k_prolong8(const double* __restrict__ xc, int nzc, int nyc, int nxc,
+__global__ void __launch_bounds__(256, 3) k_prolong8(const double* __restrict__ xc, int nzc, int nyc, int nxc,
                                                  double* __restrict__ rf, double* __restrict__ pf, int mode) {
   const size_t n = (size_t)nzc * nyc * nxc;
   size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -994,6 +994,14 @@ __global__ void __launch_bounds__(256) k_prolong8(const double* __restrict__ xc,
   const int nyc2 = nyc + 2, nzf = 2 * nzc, nyf2 = 2 * nyc + 2;
   const double a = 9.0 / 16.0, b = 3.0 / 16.0, c = 1.0 / 16.0, d = 27.0 / 64.0, ee = 9.0 / 64.0, f = 3.0 / 64.0, g = 1.0 / 64.0;
   const int km = (k2 > 1) ? k2 - 1 : k2, kp = (k2 < nzc) ? k2 + 1 : k2;      // clamped (unused values at the ends)
+  // the four fine (k,k+1) pairs of p are the only DRAM reads: issue them first so they fly during the coarse loads
+  size_t of[4]; double2 pv[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int jf = 2 * j2 - 1 + (q >> 1), i_f = 2 * i2 - 1 + (q & 1);
+    of[q] = (size_t)(2 * (k2 - 1)) + (size_t)nzf * ((size_t)jf + (size_t)nyf2 * (size_t)i_f);
+    pv[q] = (mode == 0) ? make_double2(0.0, 0.0) : *reinterpret_cast<const double2*>(pf + of[q]);
+  }
   double X[3][3][3];                                                           // [level: km,k2,kp][dj+1][di+1]
 #pragma unroll
   for (int dj = -1; dj <= 1; ++dj)
@@ -1006,8 +1014,7 @@ __global__ void __launch_bounds__(256) k_prolong8(const double* __restrict__ xc,
   for (int cj = 0; cj < 2; ++cj)
 #pragma unroll
     for (int ci = 0; ci < 2; ++ci) {
-      const int dj = cj ? +1 : -1, di = ci ? +1 : -1;
-      const int jf = 2 * j2 - 1 + cj, i_f = 2 * i2 - 1 + ci;
+      const int dj = cj ? +1 : -1, di = ci ? +1 : -1, q = cj * 2 + ci;
       const double x00 = X[1][1][1], xdd = X[1][dj + 1][di + 1], xd0 = X[1][dj + 1][1], x0d = X[1][1][di + 1];
       double vlo, vhi;
       if (k2 == 1) vlo = a * x00 + c * xdd + b * xd0 + b * x0d;                                  // fine K = 1
@@ -1016,9 +1023,8 @@ __global__ void __launch_bounds__(256) k_prolong8(const double* __restrict__ xc,
       if (k2 == nzc) { vhi = a * x00 + c * xdd + b * xd0 + b * x0d; vhi = 0.5 * vhi; }            // fine K = nzf
       else { const double y00 = X[2][1][1], ydd = X[2][dj + 1][di + 1], yd0 = X[2][dj + 1][1], y0d = X[2][1][di + 1];
              vhi = d * x00 + f * xdd + ee * xd0 + ee * x0d + ee * y00 + g * ydd + f * yd0 + f * y0d; }
-      const size_t of = (size_t)(2 * (k2 - 1)) + (size_t)nzf * ((size_t)jf + (size_t)nyf2 * (size_t)i_f);
-      if (mode == 0) *reinterpret_cast<double2*>(rf + of) = make_double2(vlo, vhi);
-      else { double2 pv = *reinterpret_cast<double2*>(pf + of); pv.x = pv.x + vlo; pv.y = pv.y + vhi; *reinterpret_cast<double2*>(pf + of) = pv; }
+      if (mode == 0) *reinterpret_cast<double2*>(rf + of[q]) = make_double2(vlo, vhi);
+      else *reinterpret_cast<double2*>(pf + of[q]) = make_double2(pv[q].x + vlo, pv[q].y + vhi);
     }
 }
 void launch_prolong(cudaStream_t st, const double* xc, int nzc, int nyc, int nxc, double* rf, double* pf, int linear, int mode) {
