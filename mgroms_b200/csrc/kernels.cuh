@@ -26,7 +26,8 @@ void launch_unpack_rows(cudaStream_t st, double* a, const double* buf, int nzl, 
 // ---- relaxation (src/mg_relax.f90:151-334) -------------------------------------------------------------
 struct ColourSet {     // columns visited by one colour of a sweep
   int istart, istep;   // i = istart, istart+istep, ... <= nx
-  int jrule;           // 0: j = 1 + mod(i+rb,2), step 2 (red-black);  1: j = jfix, step 2 (four-colour)
+  int jrule;           // 0: j = 1 + mod(i+rb,2), step 2 (red-black);  1: j = jfix, step 2 (four-colour);
+                       // 2: the single column j = jfix - 2 i (Gauss-Seidel wavefront jfix = j + 2 i)
   int rb, jfix;
   int bottom_mode;     // 0: no k=1 diagonal terms ('simple');  1: rank-1 form (two (i+1) terms from the x1 snapshot);
                        // 2: all four terms read from p (no same-colour coupling, four-colour)

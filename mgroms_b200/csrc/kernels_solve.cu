@@ -301,10 +301,14 @@ void launch_snapshot_x1(cudaStream_t st, const LevelView& L) {
   k_snapshot_x1<<<blocks_for(ncols, 256), 256, 0, st>>>(L.p, L.x1, L.nz, ncols); ++g_launches;
 }
 
-__device__ __forceinline__ int colour_jstart(const ColourSet& cs, int i) { return cs.jrule == 0 ? 1 + ((i + cs.rb) & 1) : cs.jfix; }
+// first column of row i in the set: red-black parity, fixed (four-colour), or the single column j = w - 2 i of the
+// Gauss-Seidel wavefront w = jfix (jrule 2)
+__device__ __forceinline__ int colour_jstart(const ColourSet& cs, int i) {
+  return cs.jrule == 0 ? 1 + ((i + cs.rb) & 1) : (cs.jrule == 1 ? cs.jfix : cs.jfix - 2 * i);
+}
 
 static void relax_tiling(const LevelView& L, const ColourSet& cs, int& TI, int& TJ, int& nti, int& ntj, size_t& smem) {
-  const int nyc = (L.ny + 1) / 2;                    // colour columns per visited i (upper bound)
+  const int nyc = cs.jrule == 2 ? 1 : (L.ny + 1) / 2; // columns of the set per visited i (upper bound)
   const int nvi = (L.nx - cs.istart) / cs.istep + 1; // visited i
   int tc_max = 1024 / L.nz;                          // columns per tile: ~1024 points (two 25 KB buffers per CTA leave most of the L1)
   if (tc_max < 16) tc_max = 16;
@@ -348,7 +352,7 @@ __global__ void __launch_bounds__(256, 2) k_relax_A4(LevelView L, ColourSet cs, 
         const int i = cs.istart + (t_i * TI + ci) * cs.istep;
         if (i > L.nx) continue;
         const int j = colour_jstart(cs, i) + 2 * (t_j * TJ + cj);
-        if (j > L.ny) continue;
+        if (j > L.ny || j < 1) continue;
         store_mirrored(pw, IDX3(k, j, i, nz, ny2), s_x[c * pitch + k], j, i, L.ny, L.nx, sj, si, cs.fuse_halo == 1 && cs.bottom_mode != 1);
       }
     };
@@ -368,7 +372,7 @@ __global__ void __launch_bounds__(256, 2) k_relax_A4(LevelView L, ColourSet cs, 
         const int i = cs.istart + (tile_i * TI + ci) * cs.istep;
         if (i > L.nx) continue;
         const int j = colour_jstart(cs, i) + 2 * (tile_j * TJ + cj);
-        if (j > L.ny) continue;
+        if (j > L.ny || j < 1) continue;
         const size_t idx = IDX3(k, j, i, nz, ny2);
         const double bb = b[idx], bt = bet[idx], udv = c2[idx + 1];
         const double a3 = c3[idx],           q3 = p[idx - sj + 1];
@@ -434,7 +438,7 @@ __global__ void __launch_bounds__(256, 2) k_relax_A4(LevelView L, ColourSet cs, 
         const int i = cs.istart + (tile_i * TI + ci) * cs.istep;
         if (i > L.nx) continue;
         const int j = colour_jstart(cs, i) + 2 * (tile_j * TJ + cj);
-        if (j > L.ny) continue;
+        if (j > L.ny || j < 1) continue;
         double* x = s_rhs + c * pitch; const double* bt = s_bet + c * pitch; const double* ud = s_ud + c * pitch;
         double xm = x[0] * bt[0];
         x[0] = xm;

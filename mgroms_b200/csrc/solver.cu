@@ -277,8 +277,25 @@ static int relax(int lev, int nsweeps) {
         if (cs.istart <= g.d.nx && cs.jfix <= g.d.ny) launch_relax_A(S.st, g.v, cs);
         if (!fuse) RC(fill_halo(lev, g.v.p, g.d.nz, 1));
       }
+  } else if (m == "Gauss-Seidel" || m == "GS") {
+    // relax_3D_8_GS (src/mg_relax.f90:116-148): lexicographic sweep, i outer, j inner, halo once per sweep.  Column (j,i)
+    // needs the NEW values of (j-1,i) and of row i-1 and the OLD values of (j+1,i) and of row i+1: all columns of one
+    // wavefront w = j + 2 i are independent, so a sweep is ny + 2 nx - 2 launches of the column kernel (exact, not fast).
+    bool alone = true; for (int q = 0; q < 8; ++q) alone &= g.d.neighb[q] < 0;
+    for (int it = 0; it < nsweeps; ++it) {
+      for (int w = 3; w <= g.d.ny + 2 * g.d.nx; ++w) {
+        ColourSet cs{1, 1, 2, 0, w, real_matrix ? 2 : 0, 0};
+        const int ilo = std::max(1, (w - g.d.ny + 1) / 2), ihi = std::min(g.d.nx, (w - 1) / 2);
+        if (ilo > ihi) continue;
+        cs.istart = ilo;
+        LevelView v = g.v; v.nx = ihi;                       // rows ilo..ihi only (nx is the upper bound of the row loop)
+        launch_relax_A(S.st, v, cs);
+      }
+      RC(fill_halo(lev, g.v.p, g.d.nz, 1));
+      (void)alone;
+    }
   } else {
-    return fail("relax_method '" + m + "' is not built (RB and FC are; GS is listed under SURVEY 8f-4)");
+    return fail("relax_method '" + m + "' is unknown (RB, FC, GS)");
   }
   return 0;
 }

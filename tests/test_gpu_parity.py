@@ -54,7 +54,7 @@ def test_residual_and_norm(nh, kind, nx, ny, nz):
 
 
 @pytest.mark.parametrize("kind,nx,ny,nz", CASES)
-@pytest.mark.parametrize("method", ["RB", "FC"])
+@pytest.mark.parametrize("method", ["RB", "FC", "GS"])
 def test_relax(nh, kind, nx, ny, nz, method):
     o1 = make_oracle(kind, nx, ny, nz, relax_method=method, relax_order=1)   # rank-1 formulation (what the GPU does)
     o0 = make_oracle(kind, nx, ny, nz, relax_method=method, relax_order=0)   # reference sweep order
@@ -172,13 +172,13 @@ def test_fused_prolong_equals_reference_sequence(nh, monkeypatch):
 def test_errors_are_loud(nh):
     with pytest.raises(nh.MgbError):
         nh.solve_p()                                   # before init
-    nh.set_params(relax_method="GS")
+    nh.set_params(relax_method="SOR")
     nh.nhydro_init(16, 16, 16)
     from common import geometry
     (dx, dy, zeta, h), vert = geometry("seamount", 16, 16, 16)
     nh.nhydro_matrices(dx, dy, zeta, h, None, **vert)
     with pytest.raises(nh.MgbError):
-        nh.relax(1, 1)                                 # GS is not built: must say so, not fall back
+        nh.relax(1, 1)                                 # unknown method: must say so, not fall back
     with pytest.raises(nh.MgbError):
         nh.get_field("nope")
 
@@ -224,3 +224,13 @@ def test_random_topography_config3_block_converges(nh):
     nh.compute_rhs(None, *velocities("wminus1", nx, ny, nz)); nh.solve_p()
     hg, _ = nh.history()
     assert hg[-1] <= 1e-10 and np.all(np.diff(hg) < 0), hg
+
+
+def test_gauss_seidel_solve(nh):
+    """relax_method='GS' (src/mg_relax.f90:116-148) as wavefront launches: same history as the oracle's sequential sweep."""
+    prm = dict(solver_prec=1e-9, solver_maxiter=30, relax_method="GS")
+    o = make_oracle("seamount", 32, 16, 16, **prm); o.compute_rhs(); o.solve_p()
+    make_product(nh, "seamount", 32, 16, 16, **prm)
+    nh.compute_rhs(None, *velocities("wminus1", 32, 16, 16)); nh.solve_p()
+    history_close(nh.history()[0], o.history()[0], rtol=1e-12, floor=1e-16)
+    assert relerr(nh.get_field("p"), o.get("p")) < 1e-12
