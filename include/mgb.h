@@ -119,6 +119,9 @@ void mgb_reset_launch_count(void);
  * hot kernel on the current state and reports average ms per launch.
  * out[0]=relax colour (all launches of one colour), [1]=residual+norm, [2]=restrict, [3]=prolong+add. */
 int mgb_profile_level1(int reps, double* out4);
+/* Device time (us) of one fill_halo(grid(lev)%p) -- src/mg_mpi_exchange.f90:396 -- averaged over `reps` back-to-back
+ * exchanges on the solver's stream (collective: every rank must call it with the same arguments). */
+int mgb_profile_halo(int lev, int reps, double* us_per_exchange);
 const char* mgb_version(void);
 
 #ifdef __cplusplus

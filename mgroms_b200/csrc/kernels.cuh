@@ -16,6 +16,22 @@ void launch_halo1_flagcorners(cudaStream_t st, double* a, int nzl, int ny, int n
 // two-launch multi-GPU variant for nh = 1: `pre` = physical mirrors + pack of the S/N rows; `post` = unpack + flag corners (+ x1 upkeep)
 void launch_halo1_pre(cudaStream_t st, double* a, int nzl, int ny, int nx, Halo1Flags f, double* packS, double* packN);
 void launch_halo1_post(cudaStream_t st, double* a, int nzl, int ny, int nx, Halo1Flags f, const double* recvS, const double* recvN, double* x1);
+// One-launch multi-GPU variant over NVLink peer memory (no NCCL, no fences): every rank owns a mailbox per level that its
+// neighbours have mapped (CUDA IPC).  A double travels as one 16-byte store {lo, n, hi, n} where n is the number of the
+// exchange: the receiver polls the word until both tags equal n, so the payload is its own arrival flag (each 8-byte half
+// is single-copy atomic).  The kernel (1) mirrors the physical edges and stores its boundary faces into the neighbours'
+// mailboxes, (2) polls its own mailbox and unpacks it into the halo ring (+ flag corners, + x1 upkeep).
+// Two mailbox parities make the write-after-read hazard between consecutive exchanges impossible (a neighbour can be
+// at most one exchange ahead).  The grid is capped so that all blocks are co-resident (step 2 spins).
+struct P2PBox {
+  uint4* peer[8];                     // mailbox (both parities) of the neighbour in direction q (S,E,N,W,SW,SE,NE,NW)
+  const uint4* mine;                  // my mailbox
+  unsigned long long* seq;            // exchanges completed at this level (local)
+  unsigned int* done;                 // blocks that have read *seq; the last one advances it (local)
+  int* err;                           // mapped host word: set to 1 when a poll times out
+  int nzmax;                          // slot sizing: rows are nzmax*nx, columns nzmax*ny, corners nzmax words
+};
+void launch_halo1_p2p(cudaStream_t st, double* a, int nzl, int ny, int nx, Halo1Flags f, const P2PBox& B, double* x1);
 // nh = 2 array a(nzl, -1:ny+2, -1:nx+2) (zr, zw): ring 1 mirror, ring 2 = 2A-B, corners point mirror
 void launch_halo2_phys(cudaStream_t st, double* a, int nzl, int ny, int nx, Halo1Flags f);
 void launch_halo2_flagcorners(cudaStream_t st, double* a, int nzl, int ny, int nx, Halo1Flags f);

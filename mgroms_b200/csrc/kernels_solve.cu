@@ -179,6 +179,109 @@ __global__ void k_halo1_post(double* __restrict__ a, int nzl, int ny, int nx, Ha
     x1[(size_t)j + (size_t)ny2 * i] = a[IDX3(0, j, i, nzl, ny2)];
   }
 }
+// ---- the same exchange in ONE launch over peer memory (tagged NVLink stores), see kernels.cuh -------------------------
+__device__ __forceinline__ void ll_store(uint4* dst, double v, unsigned tag) {
+  const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "r"((unsigned)u), "r"(tag), "r"((unsigned)(u >> 32)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ double ll_wait(const uint4* src, unsigned tag, int* err) {
+  unsigned lo, t0, hi, t1; int spins = 0;
+  for (;;) {
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo), "=r"(t0), "=r"(hi), "=r"(t1) : "l"(src) : "memory");
+    if (t0 == tag && t1 == tag) break;
+    if (++spins > (1 << 23)) { *err = 1; break; }          // several seconds: a lost neighbour must not hang the GPU
+    __nanosleep(64);
+  }
+  return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+}
+__global__ void __launch_bounds__(256) k_halo1_p2p(double* __restrict__ a, int nzl, int ny, int nx, Halo1Flags f, P2PBox B, double* __restrict__ x1) {
+  const int ny2 = ny + 2;
+  const size_t n_ew = (size_t)ny * nzl, n_sn = (size_t)nx * nzl;
+  const size_t row = (size_t)B.nzmax * nx, col = (size_t)B.nzmax * ny;
+  const size_t offS = 0, offE = row, offN = row + col, offW = 2 * row + col, offC = 2 * row + 2 * col;
+  const size_t stride = offC + 4 * (size_t)B.nzmax;
+  const unsigned long long s = *B.seq + 1;                 // number of this exchange; *B.seq is advanced by the last block to leave
+  const unsigned tag = (unsigned)s;
+  const size_t par = (size_t)(s & 1ull) * stride;
+  const size_t tid0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
+  const size_t n1 = 2 * n_ew + 2 * n_sn + 4 * (size_t)nzl;
+  // (1) physical mirrors in place, boundary faces into the neighbours' mailboxes
+  for (size_t e = tid0; e < n1; e += nthr) {
+    if (e < 2 * n_ew) {
+      const int side = (int)(e / n_ew); const size_t rem = e % n_ew;
+      if (side == 0) { const double v = a[IDX3(0, 1, 1, nzl, ny2) + rem];
+        if (f.west) ll_store(B.peer[3] + par + offE + rem, v, tag);
+        else { a[IDX3(0, 1, 0, nzl, ny2) + rem] = v; if (x1 && rem % nzl == 0) x1[(size_t)(1 + rem / nzl)] = v; } }
+      else { const double v = a[IDX3(0, 1, nx, nzl, ny2) + rem];
+        if (f.east) ll_store(B.peer[1] + par + offW + rem, v, tag);
+        else { a[IDX3(0, 1, nx + 1, nzl, ny2) + rem] = v; if (x1 && rem % nzl == 0) x1[(size_t)(1 + rem / nzl) + (size_t)ny2 * (nx + 1)] = v; } }
+      continue;
+    }
+    size_t e2 = e - 2 * n_ew;
+    if (e2 < 2 * n_sn) {
+      const int side = (int)(e2 / n_sn); const size_t rem = e2 % n_sn;
+      const int i = 1 + (int)(rem / nzl), k = (int)(rem % nzl);
+      if (side == 0) { const double v = a[IDX3(k, 1, i, nzl, ny2)];
+        if (f.south) ll_store(B.peer[0] + par + offN + rem, v, tag);
+        else { a[IDX3(k, 0, i, nzl, ny2)] = v; if (x1 && k == 0) x1[(size_t)ny2 * i] = v; } }
+      else { const double v = a[IDX3(k, ny, i, nzl, ny2)];
+        if (f.north) ll_store(B.peer[2] + par + offS + rem, v, tag);
+        else { a[IDX3(k, ny + 1, i, nzl, ny2)] = v; if (x1 && k == 0) x1[(size_t)(ny + 1) + (size_t)ny2 * i] = v; } }
+      continue;
+    }
+    e2 -= 2 * n_sn;
+    const int c = (int)(e2 / nzl), k = (int)(e2 % nzl);
+    const int jc = (c < 2) ? 1 : ny, ic = (c == 1 || c == 2) ? nx : 1;            // interior corner cell of corner c (SW,SE,NE,NW)
+    const int jh = (c < 2) ? 0 : ny + 1, ih = (c == 1 || c == 2) ? nx + 1 : 0;    // its halo corner
+    const double v = a[IDX3(k, jc, ic, nzl, ny2)];
+    const int diag = c == 0 ? f.sw : c == 1 ? f.se : c == 2 ? f.ne : f.nw;
+    const int sn = (c < 2) ? f.south : f.north, ew = (c == 1 || c == 2) ? f.east : f.west;
+    if (diag) ll_store(B.peer[4 + c] + par + offC + (size_t)((c + 2) & 3) * B.nzmax + k, v, tag);   // lands in the opposite corner slot
+    else if (!sn && !ew) { a[IDX3(k, jh, ih, nzl, ny2)] = v; if (x1 && k == 0) x1[(size_t)jh + (size_t)ny2 * ih] = v; }
+  }
+  // (2) poll my mailbox for the words of exchange s and unpack them
+  const uint4* __restrict__ M = B.mine + par;
+  for (size_t e = tid0; e < n1; e += nthr) {
+    if (e < 2 * n_ew) {
+      const int side = (int)(e / n_ew); const size_t rem = e % n_ew;
+      if (side == 0 && f.west) { const double v = ll_wait(M + offW + rem, tag, B.err); a[IDX3(0, 1, 0, nzl, ny2) + rem] = v; if (x1 && rem % nzl == 0) x1[(size_t)(1 + rem / nzl)] = v; }
+      if (side == 1 && f.east) { const double v = ll_wait(M + offE + rem, tag, B.err); a[IDX3(0, 1, nx + 1, nzl, ny2) + rem] = v; if (x1 && rem % nzl == 0) x1[(size_t)(1 + rem / nzl) + (size_t)ny2 * (nx + 1)] = v; }
+      continue;
+    }
+    size_t e2 = e - 2 * n_ew;
+    if (e2 < 2 * n_sn) {
+      const int side = (int)(e2 / n_sn); const size_t rem = e2 % n_sn;
+      const int i = 1 + (int)(rem / nzl), k = (int)(rem % nzl);
+      if (side == 0 && f.south) { const double v = ll_wait(M + offS + rem, tag, B.err); a[IDX3(k, 0, i, nzl, ny2)] = v; if (x1 && k == 0) x1[(size_t)ny2 * i] = v; }
+      if (side == 1 && f.north) { const double v = ll_wait(M + offN + rem, tag, B.err); a[IDX3(k, ny + 1, i, nzl, ny2)] = v; if (x1 && k == 0) x1[(size_t)(ny + 1) + (size_t)ny2 * i] = v; }
+      continue;
+    }
+    e2 -= 2 * n_sn;
+    // corners (src/mg_mpi_exchange.f90:540-598,720-743): diagonal neighbour > S/N neighbour (end of the received row) >
+    // W/E neighbour (end of the received column) > physical mirror (done in step 1)
+    const int c = (int)(e2 / nzl), k = (int)(e2 % nzl);
+    const int jh = (c < 2) ? 0 : ny + 1, ih = (c == 1 || c == 2) ? nx + 1 : 0;
+    const int diag = c == 0 ? f.sw : c == 1 ? f.se : c == 2 ? f.ne : f.nw;
+    const int sn = (c < 2) ? f.south : f.north, ew = (c == 1 || c == 2) ? f.east : f.west;
+    const size_t rowend = (size_t)k + (size_t)nzl * ((c == 1 || c == 2) ? nx - 1 : 0);   // i = nx or i = 1 of a received row
+    const size_t colend = (size_t)k + (size_t)nzl * ((c < 2) ? 0 : ny - 1);              // j = 1 or j = ny of a received column
+    double v;
+    if (diag) v = ll_wait(M + offC + (size_t)c * B.nzmax + k, tag, B.err);
+    else if (sn) v = ll_wait(M + ((c < 2) ? offS : offN) + rowend, tag, B.err);
+    else if (ew) v = ll_wait(M + ((c == 1 || c == 2) ? offE : offW) + colend, tag, B.err);
+    else continue;
+    a[IDX3(k, jh, ih, nzl, ny2)] = v;
+    if (x1 && k == 0) x1[(size_t)jh + (size_t)ny2 * ih] = v;
+  }
+  // every block has read *B.seq by now; the last one to leave advances it for the next launch
+  __syncthreads();
+  if (threadIdx.x == 0 && atomicAdd(B.done, 1u) == gridDim.x - 1) { *B.done = 0; *B.seq = s; }
+}
+void launch_halo1_p2p(cudaStream_t st, double* a, int nzl, int ny, int nx, Halo1Flags f, const P2PBox& B, double* x1) {
+  const size_t n = (size_t)2 * ny * nzl + (size_t)2 * nx * nzl + (size_t)4 * nzl;
+  unsigned nb = blocks_for(n, 256); if (nb > 592u) nb = 592u;      // 4 blocks per SM: all co-resident (the kernel spins on its peers)
+  k_halo1_p2p<<<nb, 256, 0, st>>>(a, nzl, ny, nx, f, B, x1); ++g_launches;
+}
 void launch_halo1_pre(cudaStream_t st, double* a, int nzl, int ny, int nx, Halo1Flags f, double* packS, double* packN) {
   size_t n = (size_t)2 * ny * nzl + (size_t)2 * nx * nzl + (size_t)4 * nzl;
   k_halo1_pre<<<blocks_for(n, 256), 256, 0, st>>>(a, nzl, ny, nx, f, packS, packN); ++g_launches;

@@ -36,6 +36,7 @@ struct NcclApi {
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -48,7 +49,7 @@ static int nccl_load() {
   if (!g_nccl.h) return fail(std::string("cannot load libnccl: ") + dlerror());
 #define SYM(field, name) *(void**)(&g_nccl.field) = dlsym(g_nccl.h, name); if (!g_nccl.field) return fail(std::string("libnccl lacks ") + name)
   SYM(GetUniqueId, "ncclGetUniqueId"); SYM(CommInitRank, "ncclCommInitRank"); SYM(CommDestroy, "ncclCommDestroy");
-  SYM(Send, "ncclSend"); SYM(Recv, "ncclRecv"); SYM(AllReduce, "ncclAllReduce");
+  SYM(Send, "ncclSend"); SYM(Recv, "ncclRecv"); SYM(AllReduce, "ncclAllReduce"); SYM(AllGather, "ncclAllGather");
   SYM(GroupStart, "ncclGroupStart"); SYM(GroupEnd, "ncclGroupEnd"); SYM(GetErrorString, "ncclGetErrorString");
 #undef SYM
   return 0;
@@ -71,6 +72,7 @@ struct Level {
   double *pack8[8] = {nullptr}, *unp8[8] = {nullptr};         // nh=2 staging (setup)
   double *partials = nullptr; int npartials = 0;
   Halo1Flags hf{};
+  P2PBox box{};                                               // peer-memory mailbox of this level (multi-GPU, when S.p2p)
   bool bottom_diag = true;
   double rho = 0.0;
   size_t n3() const { return (size_t)d.nz * (d.ny + 2) * (d.nx + 2); }
@@ -85,6 +87,12 @@ struct Solver {
   cudaStream_t st = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   ncclComm_t comm = nullptr;
+  // halo exchange over NVLink peer memory (CUDA IPC): one mailbox allocation per rank, mapped by its neighbours
+  bool p2p = false;
+  void* mbox = nullptr;                       // my mailbox (all levels)
+  std::vector<void*> peer_mbox;               // per rank: its mailbox mapped into this process (nullptr: self / not a neighbour)
+  unsigned long long* p2p_seq = nullptr; unsigned int* p2p_done = nullptr;   // per-level counters (local)
+  int* p2p_err_host = nullptr; int* p2p_err_dev = nullptr;                     // mapped host word raised by a timed-out wait
   double hlim = 0, theta_b = 0, theta_s = 0;
   // level-1 model arrays (k fastest) and staging for the (i,j,k) host layout
   double *ut = nullptr, *vt = nullptr, *wt = nullptr, *stage = nullptr, *flux = nullptr, *rmask = nullptr;
@@ -129,6 +137,7 @@ static int finish() {
   cudaError_t e = cudaStreamSynchronize(S.st);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return fail(std::string("CUDA failure: ") + cudaGetErrorString(e));
+  if (S.p2p_err_host && *S.p2p_err_host) { *S.p2p_err_host = 0; return fail("halo exchange timed out waiting for a neighbour GPU (peer-memory mailbox flag never raised)"); }
   return 0;
 }
 
@@ -179,6 +188,7 @@ static int exchange(Level& g, double* a, int nzl, int nh) {
 // nh = 1 with neighbours: pre kernel, one NCCL group, post kernel
 static int fill_halo1_multi(Level& g, double* a, int nzl, double* x1) {
   const int nx = g.d.nx, ny = g.d.ny;
+  if (S.p2p) { launch_halo1_p2p(S.st, a, nzl, ny, nx, g.hf, g.box, x1); return 0; }
   auto at = [&](int j, int i) { return a + (size_t)nzl * ((size_t)j + (size_t)(ny + 2) * (size_t)i); };
   launch_halo1_pre(S.st, a, nzl, ny, nx, g.hf, g.pack8[0], g.pack8[2]);
   NC(g_nccl.GroupStart());
@@ -586,6 +596,8 @@ static int correct_uvw_device() {
 static int clean() {
   if (S.st) cudaStreamSynchronize(S.st);
   drop_cycle_graph();
+  for (void* p : S.peer_mbox) if (p) cudaIpcCloseMemHandle(p);
+  if (S.p2p_err_host) cudaFreeHost(S.p2p_err_host);
   for (void* p : S.allocs) cudaFree(p);
   S.allocs.clear();
   if (S.comm && g_nccl.CommDestroy) { g_nccl.CommDestroy(S.comm); }
@@ -700,6 +712,82 @@ static int field_ref(int lev, const std::string& name, FieldRef& out) {
 // =========================================================================================================
 using namespace mgb;
 
+
+// ------------------------------------------------------------------------------------------------------
+// peer-memory mailboxes for the nh = 1 halo exchange (replaces the Isend/Irecv pairs of src/mg_mpi_exchange.f90:396-745
+// with direct NVLink stores).  Collective over all ranks; any rank that cannot map a neighbour turns it off everywhere
+// (the NCCL send/recv exchange stays as the transport then).  MGB_NO_P2P=1 forces that.
+// ------------------------------------------------------------------------------------------------------
+static int p2p_setup() {
+  S.p2p = false;
+  if (S.nranks <= 1) return 0;
+  const char* off = std::getenv("MGB_NO_P2P");
+  int ok = !(off && off[0] == '1');
+  const int nl = S.nlevs();
+  // layout (identical on every rank: the decomposition is uniform): per level 2 parities of slots of 16-byte tagged words
+  std::vector<size_t> data_off(nl, 0);
+  size_t bytes = 0;
+  auto slot_doubles = [](const LevelDims& d) { const size_t nzm = (size_t)d.nz + 1; return 2 * nzm * d.nx + 2 * nzm * d.ny + 4 * nzm; };
+  for (int q = 0; q < nl; ++q) {
+    bool any = false; for (int c = 0; c < 8; ++c) any |= S.L[q].d.neighb[c] >= 0;
+    if (!any) continue;
+    data_off[q] = bytes; bytes += ((2 * slot_doubles(S.L[q].d) * sizeof(uint4) + 255) / 256) * 256;
+  }
+  if (bytes == 0) return 0;
+  std::vector<char> handles((size_t)64 * S.nranks, 0);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  char* hbuf = nullptr;
+  { void* q = nullptr; CU(cudaMalloc(&q, (size_t)64 * S.nranks + 8)); S.allocs.push_back(q); hbuf = (char*)q; }
+  { void* q = nullptr; CU(cudaMalloc(&q, bytes)); S.allocs.push_back(q); S.mbox = q; CU(cudaMemsetAsync(q, 0, bytes, S.st)); }
+  { void* q = nullptr; CU(cudaMalloc(&q, (size_t)nl * 16)); S.allocs.push_back(q); CU(cudaMemsetAsync(q, 0, (size_t)nl * 16, S.st));
+    S.p2p_seq = (unsigned long long*)q; S.p2p_done = (unsigned int*)((char*)q + (size_t)nl * 8); }
+  CU(cudaHostAlloc((void**)&S.p2p_err_host, sizeof(int), cudaHostAllocMapped)); *S.p2p_err_host = 0;
+  CU(cudaHostGetDevicePointer((void**)&S.p2p_err_dev, S.p2p_err_host, 0));
+  cudaIpcMemHandle_t mine;
+  if (cudaIpcGetMemHandle(&mine, S.mbox) != cudaSuccess) { cudaGetLastError(); ok = 0; std::memset(&mine, 0, sizeof mine); }
+  CU(cudaMemcpyAsync(hbuf + (size_t)64 * S.rank, &mine, 64, cudaMemcpyHostToDevice, S.st));
+  NC(g_nccl.AllGather(hbuf + (size_t)64 * S.rank, hbuf, 64, ncclChar, S.comm, S.st));
+  CU(cudaMemcpyAsync(handles.data(), hbuf, handles.size(), cudaMemcpyDeviceToHost, S.st));
+  CU(cudaStreamSynchronize(S.st));
+  S.peer_mbox.assign(S.nranks, nullptr);
+  if (ok) {
+    for (int q = 0; q < nl && ok; ++q)
+      for (int c = 0; c < 8 && ok; ++c) {
+        const int nb = S.L[q].d.neighb[c];
+        if (nb < 0 || nb == S.rank || S.peer_mbox[nb]) continue;
+        cudaIpcMemHandle_t h; std::memcpy(&h, handles.data() + (size_t)64 * nb, 64);
+        void* ptr = nullptr;
+        if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+        S.peer_mbox[nb] = ptr;
+      }
+  }
+  // agree: everyone or no one
+  double* flag = (double*)(hbuf + (size_t)64 * S.nranks);   // 8 spare bytes behind the handles
+  const double mineok = ok ? 1.0 : 0.0; double allok = 0.0;
+  CU(cudaMemcpyAsync(flag, &mineok, sizeof(double), cudaMemcpyHostToDevice, S.st));
+  NC(g_nccl.AllReduce(flag, flag, 1, ncclDouble, ncclMin, S.comm, S.st));
+  CU(cudaMemcpyAsync(&allok, flag, sizeof(double), cudaMemcpyDeviceToHost, S.st));
+  CU(cudaStreamSynchronize(S.st));
+  if (allok < 0.5) {
+    if (!(off && off[0] == '1')) std::fprintf(stderr, "[mgb] rank %d: peer-memory halo exchange unavailable, using NCCL send/recv\n", S.rank);
+    return 0;
+  }
+  for (int q = 0; q < nl; ++q) {
+    Level& g = S.L[q]; P2PBox& B = g.box;
+    bool any = false; for (int c = 0; c < 8; ++c) any |= g.d.neighb[c] >= 0;
+    if (!any) continue;
+    for (int c = 0; c < 8; ++c) {
+      const int nb = g.d.neighb[c];
+      char* base = nb < 0 ? nullptr : (nb == S.rank ? (char*)S.mbox : (char*)S.peer_mbox[nb]);
+      B.peer[c] = base ? (uint4*)(base + data_off[q]) : nullptr;
+    }
+    B.mine = (const uint4*)((char*)S.mbox + data_off[q]);
+    B.seq = S.p2p_seq + q; B.done = S.p2p_done + q; B.err = S.p2p_err_dev; B.nzmax = g.d.nz + 1;
+  }
+  S.p2p = true;
+  return 0;
+}
+
 extern "C" {
 
 const char* mgb_last_error(void) { return g_err.c_str(); }
@@ -763,7 +851,7 @@ int mgb_comm_init(const void* id128) {
   RC(nccl_load());
   ncclUniqueId id; std::memcpy(&id, id128, 128);
   NC(g_nccl.CommInitRank(&S.comm, S.nranks, id, S.rank));
-  return 0;
+  return p2p_setup();
 }
 
 int mgb_matrices(const double* dx, const double* dy, const double* zeta, const double* h, const double* rmask,
@@ -874,6 +962,22 @@ int mgb_set_field(int lev, const char* name, const double* in) {
 
 long long mgb_launch_count(void) { return g_launches; }
 void mgb_reset_launch_count(void) { g_launches = 0; }
+
+int mgb_profile_halo(int lev, int reps, double* us_per_exchange) {
+  RC(check_level(lev));
+  Level& g = S.L[lev - 1];
+  cudaEvent_t a, b; CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
+  float ms = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    const int n = pass == 0 ? 3 : reps;
+    CU(cudaEventRecord(a, S.st));
+    for (int r = 0; r < n; ++r) RC(fill_halo(lev, g.v.p, g.d.nz, 1));
+    CU(cudaEventRecord(b, S.st)); CU(cudaEventSynchronize(b)); CU(cudaEventElapsedTime(&ms, a, b));
+    *us_per_exchange = 1e3 * ms / n;
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  return finish();
+}
 
 int mgb_profile_level1(int reps, double* out4) {
   if (!S.have_matrices) return fail("mgb_matrices has not been called");

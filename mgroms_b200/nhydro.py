@@ -74,6 +74,7 @@ def load(build_if_missing: bool = True):
     L.mgb_launch_count.restype = C.c_longlong
     L.mgb_reset_launch_count.restype = None
     L.mgb_profile_level1.argtypes = [C.c_int, _dp]
+    L.mgb_profile_halo.argtypes = [C.c_int, C.c_int, _dp]
     _lib = L
     return L
 
@@ -198,6 +199,12 @@ def profile_level1(reps=10):
     out = (C.c_double * 4)()
     _chk(load().mgb_profile_level1(reps, out))
     return dict(relax_colour_ms=out[0], residual_ms=out[1], restrict_ms=out[2], prolong_ms=out[3])
+
+
+def profile_halo(lev, reps=100):
+    out = C.c_double()
+    _chk(load().mgb_profile_halo(lev, reps, C.byref(out)))
+    return out.value
 
 
 # ---- topology (host only; works without a GPU) --------------------------------------------------------------------

@@ -8,17 +8,12 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 grid = {2: (2, 1), 4: (2, 2), 8: (4, 2)}[world]
 nx, ny, nz = 512, 512, 64
-nh.set_params(solver_prec=1e-10, nsmall=256)
+nh.set_params(solver_prec=1e-10, nsmall=int(sys.argv[1]) if len(sys.argv) > 1 else 8)
 nh.nhydro_init(nx, ny, nz, grid[0], grid[1], rank, device=local)
 box = [nh.comm_unique_id() if rank == 0 else None]; dist.broadcast_object_list(box, src=0); nh.comm_init(box[0])
 (dx, dy, zeta, h), vert = tc.bench_geometry("seamount", nx, ny, nz, grid[0], grid[1], rank)
 nh.nhydro_matrices(dx, dy, zeta, h, None, **vert)
-for lev in (1, 2, 3):
-    for _ in range(5): nh.fill_halo(lev, "p")
-    dist.barrier(); torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    n = 100
-    for _ in range(n): nh.fill_halo(lev, "p")
-    torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / n * 1e6
-    if rank == 0: print(f"lev {lev}: {dt:.1f} us per fill_halo call (sync per call)")
+for lev in range(1, nh.nlevs() + 1):
+    us = nh.profile_halo(lev, 200)
+    if rank == 0: print(f"lev {lev}: {us:.1f} us per fill_halo(p), back to back on the stream")
 nh.nhydro_clean(); dist.destroy_process_group()
