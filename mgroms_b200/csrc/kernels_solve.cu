@@ -413,7 +413,8 @@ __device__ __forceinline__ int colour_jstart(const ColourSet& cs, int i) {
 static void relax_tiling(const LevelView& L, const ColourSet& cs, int& TI, int& TJ, int& nti, int& ntj, size_t& smem) {
   const int nyc = cs.jrule == 2 ? 1 : (L.ny + 1) / 2; // columns of the set per visited i (upper bound)
   const int nvi = (L.nx - cs.istart) / cs.istep + 1; // visited i
-  int tc_max = 1024 / L.nz;                          // columns per tile: ~1024 points (two 25 KB buffers per CTA leave most of the L1)
+  static const int tile_pts = []() { const char* e = std::getenv("MGB_A4_TILE"); const int v = e ? std::atoi(e) : 1024; return v < 256 ? 256 : v; }();
+  int tc_max = tile_pts / L.nz;                      // columns per tile: ~1024 points (two 25 KB buffers per CTA leave most of the L1)
   if (tc_max < 16) tc_max = 16;
   if (tc_max > 1024) tc_max = 1024;
   while (tc_max > 1 && (size_t)tc_max * (L.nz + 1) * 3 * sizeof(double) > 100 * 1024) tc_max /= 2;
@@ -431,15 +432,29 @@ static void relax_tiling(const LevelView& L, const ColourSet& cs, int& TI, int& 
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-__global__ void __launch_bounds__(256, 2) k_relax_A4(LevelView L, ColourSet cs, int TI, int TJ, int ntj, int ntiles) {
+// NZC > 0: nz known at compile time (power of two) so that every k/j offset of the 27 operand addresses is an immediate
+// and e -> (k, column) is a shift; 0: generic.  tj_shift >= 0 when TJ is a power of two.  All element indices are 32-bit
+// (a level holds < 2^31 points per GPU): one IMAD.WIDE per operand array instead of 64-bit add chains.
+template <int MINB, int NZC>
+__global__ void __launch_bounds__(256, MINB) k_relax_A4(LevelView L, ColourSet cs, int TI, int TJ, int ntj, int ntiles, int tj_shift) {
   extern __shared__ __align__(16) double sm[];
-  const int nz = L.nz, ny2 = L.ny + 2, pitch = nz + 1;
+  const int nz = NZC ? NZC : L.nz, ny2 = L.ny + 2, pitch = nz + 1;
   const int TC = TI * TJ;
-  const size_t bufsz = (size_t)3 * TC * pitch;
+  const int bufsz = 3 * TC * pitch;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int sj = nz; const size_t si = (size_t)nz * ny2;
+  const int sj = nz; const int si = nz * ny2;
   const int nelem = TC * nz;
   constexpr int NPROD = 7 * 32;
+  // element e of a tile -> (k, column c) -> (ci, cj) -> (i, j); returns false for padding columns
+  auto locate = [&](int e, int tile_i, int tile_j, int& k, int& c, int& i, int& j) -> bool {
+    if (NZC) { k = e & (NZC - 1); c = e / (NZC ? NZC : 1); } else { k = e % nz; c = e / nz; }
+    int ci, cj;
+    if (tj_shift >= 0) { ci = c >> tj_shift; cj = c & (TJ - 1); } else { ci = c / TJ; cj = c - ci * TJ; }
+    i = cs.istart + (tile_i * TI + ci) * cs.istep;
+    if (i > L.nx) return false;
+    j = colour_jstart(cs, i) + 2 * (tile_j * TJ + cj);
+    return j <= L.ny && j >= 1;
+  };
   // barrier ids: 1,2 = buffer b full ; 3,4 = buffer b empty
   if (warp < 7) {
     const double* __restrict__ p = L.p; const double* __restrict__ b = L.b;
@@ -447,22 +462,22 @@ __global__ void __launch_bounds__(256, 2) k_relax_A4(LevelView L, ColourSet cs, 
     const double* __restrict__ c5 = L.cA[4]; const double* __restrict__ c6 = L.cA[5]; const double* __restrict__ c7 = L.cA[6];
     const double* __restrict__ c8 = L.cA[7]; const double* __restrict__ bet = L.bet;
     double* __restrict__ pw = L.p;
+    const bool mirror = cs.fuse_halo == 1 && cs.bottom_mode != 1;
     auto writeback = [&](const double* s_x, int t) {         // coalesced along k; final values also go to the Neumann halo
       const int t_j = t % ntj, t_i = t / ntj;
       for (int e = threadIdx.x; e < nelem; e += NPROD) {
-        const int k = e % nz, c = e / nz;
-        const int ci = c / TJ, cj = c % TJ;
-        const int i = cs.istart + (t_i * TI + ci) * cs.istep;
-        if (i > L.nx) continue;
-        const int j = colour_jstart(cs, i) + 2 * (t_j * TJ + cj);
-        if (j > L.ny || j < 1) continue;
-        store_mirrored(pw, IDX3(k, j, i, nz, ny2), s_x[c * pitch + k], j, i, L.ny, L.nx, sj, si, cs.fuse_halo == 1 && cs.bottom_mode != 1);
+        int k, c, i, j;
+        if (!locate(e, t_i, t_j, k, c, i, j)) continue;
+        const int idx = k + nz * (j + ny2 * i);
+        const double v = s_x[c * pitch + k];
+        if (!mirror) pw[idx] = v;
+        else store_mirrored(pw, (size_t)idx, v, j, i, L.ny, L.nx, (size_t)sj, (size_t)si, true);
       }
     };
     int n = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
       const int bsel = n & 1;
-      double* s_rhs = sm + bsel * bufsz; double* s_bet = s_rhs + (size_t)TC * pitch; double* s_ud = s_bet + (size_t)TC * pitch;
+      double* s_rhs = sm + bsel * bufsz; double* s_bet = s_rhs + TC * pitch; double* s_ud = s_bet + TC * pitch;
       if (n >= 2) {                                         // tile n-2 sits solved in this buffer: write it back, then reuse the buffer
         named_bar_sync(3 + bsel, 256);
         writeback(s_rhs, tile - 2 * (int)gridDim.x);
@@ -470,13 +485,10 @@ __global__ void __launch_bounds__(256, 2) k_relax_A4(LevelView L, ColourSet cs, 
       }
       const int tile_j = tile % ntj, tile_i = tile / ntj;
       for (int e = threadIdx.x; e < nelem; e += NPROD) {
-        const int k = e % nz, c = e / nz;
-        const int ci = c / TJ, cj = c % TJ;
-        const int i = cs.istart + (tile_i * TI + ci) * cs.istep;
-        if (i > L.nx) continue;
-        const int j = colour_jstart(cs, i) + 2 * (tile_j * TJ + cj);
-        if (j > L.ny || j < 1) continue;
-        const size_t idx = IDX3(k, j, i, nz, ny2);
+        int k, c, i, j;
+        if (!locate(e, tile_i, tile_j, k, c, i, j)) continue;
+        const int idx = k + nz * (j + ny2 * i);
+        const int im = idx - si, ip = idx + si;             // same k, j in rows i-1 / i+1
         const double bb = b[idx], bt = bet[idx], udv = c2[idx + 1];
         const double a3 = c3[idx],           q3 = p[idx - sj + 1];
         const double a3n = c3[idx + sj - 1], q3n = p[idx + sj - 1];
@@ -484,12 +496,12 @@ __global__ void __launch_bounds__(256, 2) k_relax_A4(LevelView L, ColourSet cs, 
         const double a4n = c4[idx + sj],     q4n = p[idx + sj];
         const double a5 = c5[idx],           q5 = p[idx - sj - 1];
         const double a5n = c5[idx + sj + 1], q5n = p[idx + sj + 1];
-        const double a6 = c6[idx],           q6 = p[idx - si + 1];
-        const double a6n = c6[idx + si - 1], q6n = p[idx + si - 1];
-        const double a7 = c7[idx],           q7 = p[idx - si];
-        const double a7n = c7[idx + si],     q7n = p[idx + si];
-        const double a8 = c8[idx],           q8 = p[idx - si - 1];
-        const double a8n = c8[idx + si + 1], q8n = p[idx + si + 1];
+        const double a6 = c6[idx],           q6 = p[im + 1];
+        const double a6n = c6[ip - 1],       q6n = p[ip - 1];
+        const double a7 = c7[idx],           q7 = p[im];
+        const double a7n = c7[ip],           q7n = p[ip];
+        const double a8 = c8[idx],           q8 = p[im - 1];
+        const double a8n = c8[ip + 1],       q8n = p[ip + 1];
         const bool lo = (k > 0), hi = (k < nz - 1);
         double acc = bb;
         if (hi) acc = acc - a3 * q3;
@@ -506,19 +518,20 @@ __global__ void __launch_bounds__(256, 2) k_relax_A4(LevelView L, ColourSet cs, 
         if (hi) acc = acc - a8n * q8n;
         if (k == 0) {
           if (cs.bottom_mode == 1) {
-            const size_t c2d = (size_t)j + (size_t)ny2 * i;
+            const int c2d = j + ny2 * i;
             acc = acc - L.c5b[c2d - 1 + ny2] * L.x1[c2d - 1 + ny2];
             acc = acc - L.c8b[c2d + 1 + ny2] * L.x1[c2d + 1 + ny2];
           } else if (cs.bottom_mode == 2) {
-            acc = acc - a5 * p[idx + sj - si];
-            acc = acc - c5[idx - sj + si] * p[idx - sj + si];
-            acc = acc - a8 * p[idx - sj - si];
-            acc = acc - c8[idx + sj + si] * p[idx + sj + si];
+            acc = acc - a5 * p[im + sj];
+            acc = acc - c5[ip - sj] * p[ip - sj];
+            acc = acc - a8 * p[im - sj];
+            acc = acc - c8[ip + sj] * p[ip + sj];
           }
         }
-        s_rhs[c * pitch + k] = acc;
-        s_bet[c * pitch + k] = bt;
-        s_ud[c * pitch + k] = hi ? udv : 0.0;
+        const int so = c * pitch + k;
+        s_rhs[so] = acc;
+        s_bet[so] = bt;
+        s_ud[so] = hi ? udv : 0.0;
       }
       __threadfence_block();
       named_bar_arrive(1 + bsel, 256);                      // buffer full
@@ -533,7 +546,7 @@ __global__ void __launch_bounds__(256, 2) k_relax_A4(LevelView L, ColourSet cs, 
     int n = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
       const int bsel = n & 1;
-      double* s_rhs = sm + bsel * bufsz; const double* s_bet = s_rhs + (size_t)TC * pitch; const double* s_ud = s_bet + (size_t)TC * pitch;
+      double* s_rhs = sm + bsel * bufsz; const double* s_bet = s_rhs + TC * pitch; const double* s_ud = s_bet + TC * pitch;
       named_bar_sync(1 + bsel, 256);                        // wait for the producers
       const int tile_j = tile % ntj, tile_i = tile / ntj;
       for (int c = lane; c < TC; c += 32) {
@@ -555,12 +568,34 @@ __global__ void __launch_bounds__(256, 2) k_relax_A4(LevelView L, ColourSet cs, 
     }
   }
 }
+template <int MINB>
+static void launch_A4_nz(cudaStream_t st, const LevelView& L, const ColourSet& cs, int grid, size_t smem, int TI, int TJ, int ntj, int ntiles, int tj_shift) {
+  switch (L.nz) {
+    case 128: k_relax_A4<MINB, 128><<<grid, 256, smem, st>>>(L, cs, TI, TJ, ntj, ntiles, tj_shift); break;
+    case 64: k_relax_A4<MINB, 64><<<grid, 256, smem, st>>>(L, cs, TI, TJ, ntj, ntiles, tj_shift); break;
+    case 32: k_relax_A4<MINB, 32><<<grid, 256, smem, st>>>(L, cs, TI, TJ, ntj, ntiles, tj_shift); break;
+    case 16: k_relax_A4<MINB, 16><<<grid, 256, smem, st>>>(L, cs, TI, TJ, ntj, ntiles, tj_shift); break;
+    default: k_relax_A4<MINB, 0><<<grid, 256, smem, st>>>(L, cs, TI, TJ, ntj, ntiles, tj_shift); break;
+  }
+}
+template <int MINB> static void a4_attrs() {
+  cudaFuncSetAttribute(k_relax_A4<MINB, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_relax_A4<MINB, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_relax_A4<MINB, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_relax_A4<MINB, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_relax_A4<MINB, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+}
 void launch_relax_A(cudaStream_t st, const LevelView& L, const ColourSet& cs) {
   int TI, TJ, nti, ntj; size_t smem1;
   relax_tiling(L, cs, TI, TJ, nti, ntj, smem1);
   const int ntiles = nti * ntj;
-  const int grid = ntiles < 296 ? ntiles : 296;        // persistent: two CTAs per SM
-  k_relax_A4<<<grid, 256, 2 * smem1, st>>>(L, cs, TI, TJ, ntj, ntiles); ++g_launches;
+  static const int minb = []() { const char* e = std::getenv("MGB_A4_CTAS"); const int v = e ? std::atoi(e) : 3; return v < 2 ? 2 : (v > 3 ? 3 : v); }();
+  const int cap = 148 * minb;
+  const int grid = ntiles < cap ? ntiles : cap;        // persistent: minb CTAs per SM
+  int tj_shift = -1; for (int q = 0; q < 12; ++q) if ((1 << q) == TJ) tj_shift = q;
+  if (minb == 2) launch_A4_nz<2>(st, L, cs, grid, 2 * smem1, TI, TJ, ntj, ntiles, tj_shift);
+  else launch_A4_nz<3>(st, L, cs, grid, 2 * smem1, TI, TJ, ntj, ntiles, tj_shift);
+  ++g_launches;
 }
 
 // Kernel B: the sequential part of the red-black bottom coupling, on the 2-D k=1 plane only.
@@ -880,7 +915,7 @@ __global__ void __launch_bounds__(1024) k_relax_small(LevelView L, int nsweeps, 
   if (all_smem) for (int e = threadIdx.x; e < n3; e += blockDim.x) L.p[e] = p[e];
 }
 void kernels_init() {
-  cudaFuncSetAttribute(k_relax_A4, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  a4_attrs<2>(); a4_attrs<3>();
   cudaFuncSetAttribute(k_relax_B<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   cudaFuncSetAttribute(k_relax_B<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   cudaFuncSetAttribute(k_relax_B<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
