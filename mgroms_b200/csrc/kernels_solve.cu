@@ -676,24 +676,35 @@ void launch_relax_B(cudaStream_t st, const LevelView& L, const ColourSet& cs) {
 // Kernel C: p(:,j,i) += s(j,i) * g(:,j,i) on the columns of the colour
 __global__ void __launch_bounds__(256) k_relax_C(LevelView L, ColourSet cs, int nyc) {
   const int nz = L.nz, ny2 = L.ny + 2;
-  // one i per blockIdx.y ; x dimension covers (k, colour column)
+  // one i per blockIdx.y ; a block covers 4*256 consecutive (k, colour column) elements, four per thread (loads first)
   const int i = cs.istart + blockIdx.y * cs.istep;
   const int js = colour_jstart(cs, i);
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= nyc * nz) return;
-  const int k = e % nz, jc = e / nz;
-  const int j = js + 2 * jc;
-  if (j > L.ny) return;
-  const double sv = L.s[(size_t)j + (size_t)ny2 * i];
-  const size_t idx = IDX3(k, j, i, nz, ny2);
-  const double v = L.p[idx] + sv * L.g[idx];
-  const bool edge = (cs.fuse_halo == 1) && (i == 1 || i == L.nx || j <= 2 || j >= L.ny - 1);
-  if (!edge) {
-    L.p[idx] = v;
-    if (k == 0 && cs.fuse_halo) L.x1[(size_t)j + (size_t)ny2 * i] = v;   // fuse_halo == 2: keep x1 current, halo done by the exchange
-  } else {
-    store_mirrored(L.p, idx, v, j, i, L.ny, L.nx, (size_t)nz, (size_t)nz * ny2, true);
-    if (k == 0) store_mirrored(L.x1, (size_t)j + (size_t)ny2 * i, v, j, i, L.ny, L.nx, 1, (size_t)ny2, true);
+  const int n = nyc * nz;
+  const int e0 = blockIdx.x * 1024 + threadIdx.x;
+  int idx[4], jj[4]; double pv[4], gv[4], sv[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int e = e0 + 256 * u;
+    const int jc = e / nz, k = e - jc * nz;
+    jj[u] = js + 2 * jc;
+    const bool ok = e < n && jj[u] <= L.ny;
+    idx[u] = ok ? k + nz * (jj[u] + ny2 * i) : -1;
+    if (ok) { pv[u] = L.p[idx[u]]; gv[u] = L.g[idx[u]]; sv[u] = L.s[jj[u] + ny2 * i]; }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    if (idx[u] < 0) continue;
+    const int j = jj[u];
+    const double v = pv[u] + sv[u] * gv[u];
+    const bool k0 = (idx[u] - nz * (j + ny2 * i)) == 0;
+    const bool edge = (cs.fuse_halo == 1) && (i == 1 || i == L.nx || j <= 2 || j >= L.ny - 1);
+    if (!edge) {
+      L.p[idx[u]] = v;
+      if (k0 && cs.fuse_halo) L.x1[j + ny2 * i] = v;   // fuse_halo == 2: keep x1 current, halo done by the exchange
+    } else {
+      store_mirrored(L.p, (size_t)idx[u], v, j, i, L.ny, L.nx, (size_t)nz, (size_t)nz * ny2, true);
+      if (k0) store_mirrored(L.x1, (size_t)j + (size_t)ny2 * i, v, j, i, L.ny, L.nx, 1, (size_t)ny2, true);
+    }
   }
 }
 // Kernels B and C fused (neighbour-free levels): a CTA owns one chunk of rows (c0..c1) and a block of 2*TJ columns.
@@ -772,7 +783,7 @@ void launch_relax_BC(cudaStream_t st, const LevelView& L, const ColourSet& cs, c
 void launch_relax_C(cudaStream_t st, const LevelView& L, const ColourSet& cs) {
   const int nyc = (L.ny + 1) / 2;
   const int nvi = (L.nx - cs.istart) / cs.istep + 1;
-  dim3 grid(blocks_for((size_t)nyc * L.nz, 256), nvi);
+  dim3 grid(blocks_for((size_t)nyc * L.nz, 1024), nvi);
   k_relax_C<<<grid, 256, 0, st>>>(L, cs, nyc); ++g_launches;
 }
 
@@ -965,11 +976,13 @@ __device__ __forceinline__ double block_sum_256(double v, double* s_red) {
 }
 
 // one block handles a chunk of one i-slab: elements (k, j) flattened, j = 1..ny
+template <int NZC>   // NZC > 0: nz at compile time (power of two): immediates for the k/j offsets, shifts for e -> (k, j)
 __global__ void __launch_bounds__(256, 3) k_residual(LevelView L, int real_matrix, int chunks_per_i, double* __restrict__ partials) {
   __shared__ double s_red[8];
-  const int nz = L.nz, ny = L.ny, ny2 = ny + 2;
+  const int nz = NZC ? NZC : L.nz, ny = L.ny, ny2 = ny + 2;
   const int i = 1 + blockIdx.x / chunks_per_i, chunk = blockIdx.x % chunks_per_i;
-  const int sj = nz; const size_t si = (size_t)nz * ny2;
+  const int sj = nz; const int si = nz * ny2;
+  const int base_i = nz * (1 + ny2 * i);                 // element index of (k=0, j=1, i): the slab is contiguous in (k, j)
   const double* __restrict__ p = L.p; const double* __restrict__ b = L.b;
   const double* __restrict__ c1 = L.cA[0]; const double* __restrict__ c2 = L.cA[1]; const double* __restrict__ c3 = L.cA[2];
   const double* __restrict__ c4 = L.cA[3]; const double* __restrict__ c5 = L.cA[4]; const double* __restrict__ c6 = L.cA[5];
@@ -980,8 +993,8 @@ __global__ void __launch_bounds__(256, 3) k_residual(LevelView L, int real_matri
   const int e0 = chunk * per_chunk, e1 = min(nelem, e0 + per_chunk);
   double sum = 0.0;
   for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
-    const int k = e % nz, j = 1 + e / nz;
-    const size_t idx = IDX3(k, j, i, nz, ny2);
+    const int k = NZC ? (e & (NZC - 1)) : e % nz;
+    const int idx = base_i + e;
     const double bb = b[idx];
     const double a1 = c1[idx],           q1v = p[idx];
     const double a2 = c2[idx],           q2 = p[idx - 1];
@@ -1043,7 +1056,14 @@ static int residual_chunks(const LevelView& L) {
 int residual_num_partials(const LevelView& L) { return L.nx * residual_chunks(L); }
 void launch_residual(cudaStream_t st, const LevelView& L, int real_matrix, double* partials, double* sum_out) {
   const int chunks = residual_chunks(L);
-  k_residual<<<L.nx * chunks, 256, 0, st>>>(L, real_matrix, chunks, partials); ++g_launches;
+  switch (L.nz) {
+    case 128: k_residual<128><<<L.nx * chunks, 256, 0, st>>>(L, real_matrix, chunks, partials); break;
+    case 64: k_residual<64><<<L.nx * chunks, 256, 0, st>>>(L, real_matrix, chunks, partials); break;
+    case 32: k_residual<32><<<L.nx * chunks, 256, 0, st>>>(L, real_matrix, chunks, partials); break;
+    case 16: k_residual<16><<<L.nx * chunks, 256, 0, st>>>(L, real_matrix, chunks, partials); break;
+    default: k_residual<0><<<L.nx * chunks, 256, 0, st>>>(L, real_matrix, chunks, partials); break;
+  }
+  ++g_launches;
   k_reduce_final<<<1, 256, 0, st>>>(partials, L.nx * chunks, sum_out); ++g_launches;
 }
 __global__ void __launch_bounds__(256) k_sumsq(const double* __restrict__ a, int nz, int ny, int chunks_per_i, double* __restrict__ partials) {
