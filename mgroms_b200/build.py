@@ -38,6 +38,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
            "-fmad=false", "-Xcompiler", "-fPIC", "-shared", "-ccbin", ccbin,
            "-o", SO] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
+    if os.environ.get("MGB_BUILD_DEFS"):
+        cmd[1:1] = ["-D" + d for d in os.environ["MGB_BUILD_DEFS"].split(",")]
     if verbose:
         cmd.insert(1, "-Xptxas"); cmd.insert(2, "-v")
         print(" ".join(cmd))

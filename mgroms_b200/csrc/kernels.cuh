@@ -59,6 +59,10 @@ void launch_relax_BC(cudaStream_t st, const LevelView& L, const ColourSet& cs, c
 // whole relax(lev, nsweeps) of a small, neighbour-free level in one single-CTA launch (red-black only)
 bool relax_small_supported(const LevelView& L);
 void launch_relax_small(cudaStream_t st, const LevelView& L, int nsweeps, int rank1);
+// whole relax(lev, nsweeps) of a mid-size, neighbour-free level in one cooperative launch with software grid barriers
+// (red-black only); `bar` = two zeroed device words owned by the level
+bool relax_mid_supported(const LevelView& L);
+void launch_relax_mid(cudaStream_t st, const LevelView& L, int nsweeps, int rank1, unsigned* bar);
 
 // ---- residual + norm (src/mg_relax.f90:337-515) ----------------------------------------------------------
 // r = b - A p on the interior; partial sums of r^2 per block into `partials`, then reduced in fixed order to *sum_out.

@@ -15,6 +15,15 @@ long long g_launches = 0;
 
 static inline unsigned blocks_for(size_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
 
+// one launch path for every kernel of this file (counts the launches for mgb_launch_count)
+template <typename... KArgs, typename... Args>
+static void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+  ++g_launches;
+}
+
 // =====================================================================================================
 // generic helpers
 // =====================================================================================================
@@ -35,9 +44,9 @@ static unsigned capped_blocks(size_t n, unsigned threads) {
   const size_t cap = 148 * 16;
   return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
 }
-void launch_fill(cudaStream_t st, double* a, double v, size_t n) { if (!n) return; k_fill<<<capped_blocks(n, 256), 256, 0, st>>>(a, v, n); ++g_launches; }
-void launch_copy(cudaStream_t st, double* d, const double* s, size_t n) { if (!n) return; k_copy<<<capped_blocks(n, 256), 256, 0, st>>>(d, s, n); ++g_launches; }
-void launch_axpy_all(cudaStream_t st, double* y, const double* x, size_t n) { if (!n) return; k_axpy_all<<<capped_blocks(n, 256), 256, 0, st>>>(y, x, n); ++g_launches; }
+void launch_fill(cudaStream_t st, double* a, double v, size_t n) { if (!n) return; launch_k(k_fill, capped_blocks(n, 256), 256, 0, st, a, v, n); }
+void launch_copy(cudaStream_t st, double* d, const double* s, size_t n) { if (!n) return; launch_k(k_copy, capped_blocks(n, 256), 256, 0, st, d, s, n); }
+void launch_axpy_all(cudaStream_t st, double* y, const double* x, size_t n) { if (!n) return; launch_k(k_axpy_all, capped_blocks(n, 256), 256, 0, st, y, x, n); }
 
 // p += r on the halo ring (j in {0,ny+1} or i in {0,nx+1})
 __global__ void k_add_halo_ring(double* __restrict__ p, const double* __restrict__ r, int nz, int ny, int nx) {
@@ -59,7 +68,7 @@ __global__ void k_add_halo_ring(double* __restrict__ p, const double* __restrict
 }
 void launch_add_halo_ring(cudaStream_t st, double* p, const double* r, int nz, int ny, int nx) {
   size_t n = (size_t)2 * (ny + 2) * nz + (size_t)2 * nx * nz;
-  k_add_halo_ring<<<blocks_for(n, 256), 256, 0, st>>>(p, r, nz, ny, nx); ++g_launches;
+  launch_k(k_add_halo_ring, blocks_for(n, 256), 256, 0, st, p, r, nz, ny, nx);
 }
 
 // =====================================================================================================
@@ -94,7 +103,7 @@ __global__ void k_halo1_phys(double* __restrict__ a, int nzl, int ny, int nx, Ha
 }
 void launch_halo1_phys(cudaStream_t st, double* a, int nzl, int ny, int nx, Halo1Flags f) {
   size_t n = (size_t)2 * ny * nzl + (size_t)2 * nx * nzl + (size_t)4 * nzl;
-  k_halo1_phys<<<blocks_for(n, 256), 256, 0, st>>>(a, nzl, ny, nx, f); ++g_launches;
+  launch_k(k_halo1_phys, blocks_for(n, 256), 256, 0, st, a, nzl, ny, nx, f);
 }
 // corners next to a physical wall but with one lateral neighbour: copy from the halo row/column just received
 __global__ void k_halo1_flagcorners(double* __restrict__ a, int nzl, int ny, int nx, Halo1Flags f) {
@@ -108,7 +117,7 @@ __global__ void k_halo1_flagcorners(double* __restrict__ a, int nzl, int ny, int
   if (c == 3 && !f.nw) { if (f.north) a[IDX3(k, ny + 1, 0, nzl, ny2)] = a[IDX3(k, ny + 1, 1, nzl, ny2)]; else if (f.west) a[IDX3(k, ny + 1, 0, nzl, ny2)] = a[IDX3(k, ny, 0, nzl, ny2)]; }
 }
 void launch_halo1_flagcorners(cudaStream_t st, double* a, int nzl, int ny, int nx, Halo1Flags f) {
-  k_halo1_flagcorners<<<blocks_for((size_t)4 * nzl, 128), 128, 0, st>>>(a, nzl, ny, nx, f); ++g_launches;
+  launch_k(k_halo1_flagcorners, blocks_for((size_t)4 * nzl, 128), 128, 0, st, a, nzl, ny, nx, f);
 }
 
 // Multi-GPU halo of an nh=1 field in two launches around the NCCL group:
@@ -280,15 +289,15 @@ __global__ void __launch_bounds__(256) k_halo1_p2p(double* __restrict__ a, int n
 void launch_halo1_p2p(cudaStream_t st, double* a, int nzl, int ny, int nx, Halo1Flags f, const P2PBox& B, double* x1) {
   const size_t n = (size_t)2 * ny * nzl + (size_t)2 * nx * nzl + (size_t)4 * nzl;
   unsigned nb = blocks_for(n, 256); if (nb > 592u) nb = 592u;      // 4 blocks per SM: all co-resident (the kernel spins on its peers)
-  k_halo1_p2p<<<nb, 256, 0, st>>>(a, nzl, ny, nx, f, B, x1); ++g_launches;
+  launch_k(k_halo1_p2p, nb, 256, 0, st, a, nzl, ny, nx, f, B, x1);
 }
 void launch_halo1_pre(cudaStream_t st, double* a, int nzl, int ny, int nx, Halo1Flags f, double* packS, double* packN) {
   size_t n = (size_t)2 * ny * nzl + (size_t)2 * nx * nzl + (size_t)4 * nzl;
-  k_halo1_pre<<<blocks_for(n, 256), 256, 0, st>>>(a, nzl, ny, nx, f, packS, packN); ++g_launches;
+  launch_k(k_halo1_pre, blocks_for(n, 256), 256, 0, st, a, nzl, ny, nx, f, packS, packN);
 }
 void launch_halo1_post(cudaStream_t st, double* a, int nzl, int ny, int nx, Halo1Flags f, const double* recvS, const double* recvN, double* x1) {
   size_t n = (size_t)2 * nx * nzl + (size_t)4 * nzl + (size_t)2 * ny;
-  k_halo1_post<<<blocks_for(n, 256), 256, 0, st>>>(a, nzl, ny, nx, f, recvS, recvN, x1); ++g_launches;
+  launch_k(k_halo1_post, blocks_for(n, 256), 256, 0, st, a, nzl, ny, nx, f, recvS, recvN, x1);
 }
 
 // =====================================================================================================
@@ -330,7 +339,7 @@ __global__ void k_halo2_phys(double* __restrict__ a, int nzl, int ny, int nx, Ha
 }
 void launch_halo2_phys(cudaStream_t st, double* a, int nzl, int ny, int nx, Halo1Flags f) {
   size_t n = (size_t)2 * ny * nzl + (size_t)2 * nx * nzl + (size_t)4 * nzl;
-  k_halo2_phys<<<blocks_for(n, 256), 256, 0, st>>>(a, nzl, ny, nx, f); ++g_launches;
+  launch_k(k_halo2_phys, blocks_for(n, 256), 256, 0, st, a, nzl, ny, nx, f);
 }
 __global__ void k_halo2_flagcorners(double* __restrict__ a, int nzl, int ny, int nx, Halo1Flags f) {
   const int ny4 = ny + 4;
@@ -345,7 +354,7 @@ __global__ void k_halo2_flagcorners(double* __restrict__ a, int nzl, int ny, int
   }
 }
 void launch_halo2_flagcorners(cudaStream_t st, double* a, int nzl, int ny, int nx, Halo1Flags f) {
-  k_halo2_flagcorners<<<blocks_for((size_t)4 * nzl, 128), 128, 0, st>>>(a, nzl, ny, nx, f); ++g_launches;
+  launch_k(k_halo2_flagcorners, blocks_for((size_t)4 * nzl, 128), 128, 0, st, a, nzl, ny, nx, f);
 }
 
 // pack a rectangular (j0..j0+nrows-1) x (i0..i0+ncols-1) patch of an array with halo width nh into a dense buffer
@@ -367,11 +376,11 @@ __global__ void k_unpack_rows(double* __restrict__ a, const double* __restrict__
 // j0,i0 are Fortran indices (may be <= 0 for halo cells); nyh = ny + 2*nh
 void launch_pack_rows(cudaStream_t st, const double* a, double* buf, int nzl, int ny, int nx, int nh, int j0, int nrows, int i0, int ncols) {
   size_t n = (size_t)nzl * nrows * ncols; (void)nx;
-  k_pack_rows<<<blocks_for(n, 256), 256, 0, st>>>(a, buf, nzl, ny + 2 * nh, nh, j0, nrows, i0, ncols); ++g_launches;
+  launch_k(k_pack_rows, blocks_for(n, 256), 256, 0, st, a, buf, nzl, ny + 2 * nh, nh, j0, nrows, i0, ncols);
 }
 void launch_unpack_rows(cudaStream_t st, double* a, const double* buf, int nzl, int ny, int nx, int nh, int j0, int nrows, int i0, int ncols) {
   size_t n = (size_t)nzl * nrows * ncols; (void)nx;
-  k_unpack_rows<<<blocks_for(n, 256), 256, 0, st>>>(a, buf, nzl, ny + 2 * nh, nh, j0, nrows, i0, ncols); ++g_launches;
+  launch_k(k_unpack_rows, blocks_for(n, 256), 256, 0, st, a, buf, nzl, ny + 2 * nh, nh, j0, nrows, i0, ncols);
 }
 
 // =====================================================================================================
@@ -401,7 +410,7 @@ __global__ void k_snapshot_x1(const double* __restrict__ p, double* __restrict__
 }
 void launch_snapshot_x1(cudaStream_t st, const LevelView& L) {
   size_t ncols = (size_t)(L.ny + 2) * (L.nx + 2);
-  k_snapshot_x1<<<blocks_for(ncols, 256), 256, 0, st>>>(L.p, L.x1, L.nz, ncols); ++g_launches;
+  launch_k(k_snapshot_x1, blocks_for(ncols, 256), 256, 0, st, L.p, L.x1, L.nz, ncols);
 }
 
 // first column of row i in the set: red-black parity, fixed (four-colour), or the single column j = w - 2 i of the
@@ -571,11 +580,11 @@ __global__ void __launch_bounds__(256, MINB) k_relax_A4(LevelView L, ColourSet c
 template <int MINB>
 static void launch_A4_nz(cudaStream_t st, const LevelView& L, const ColourSet& cs, int grid, size_t smem, int TI, int TJ, int ntj, int ntiles, int tj_shift) {
   switch (L.nz) {
-    case 128: k_relax_A4<MINB, 128><<<grid, 256, smem, st>>>(L, cs, TI, TJ, ntj, ntiles, tj_shift); break;
-    case 64: k_relax_A4<MINB, 64><<<grid, 256, smem, st>>>(L, cs, TI, TJ, ntj, ntiles, tj_shift); break;
-    case 32: k_relax_A4<MINB, 32><<<grid, 256, smem, st>>>(L, cs, TI, TJ, ntj, ntiles, tj_shift); break;
-    case 16: k_relax_A4<MINB, 16><<<grid, 256, smem, st>>>(L, cs, TI, TJ, ntj, ntiles, tj_shift); break;
-    default: k_relax_A4<MINB, 0><<<grid, 256, smem, st>>>(L, cs, TI, TJ, ntj, ntiles, tj_shift); break;
+    case 128: launch_k(k_relax_A4<MINB, 128>, grid, 256, smem, st, L, cs, TI, TJ, ntj, ntiles, tj_shift); break;
+    case 64: launch_k(k_relax_A4<MINB, 64>, grid, 256, smem, st, L, cs, TI, TJ, ntj, ntiles, tj_shift); break;
+    case 32: launch_k(k_relax_A4<MINB, 32>, grid, 256, smem, st, L, cs, TI, TJ, ntj, ntiles, tj_shift); break;
+    case 16: launch_k(k_relax_A4<MINB, 16>, grid, 256, smem, st, L, cs, TI, TJ, ntj, ntiles, tj_shift); break;
+    default: launch_k(k_relax_A4<MINB, 0>, grid, 256, smem, st, L, cs, TI, TJ, ntj, ntiles, tj_shift); break;
   }
 }
 template <int MINB> static void a4_attrs() {
@@ -595,7 +604,6 @@ void launch_relax_A(cudaStream_t st, const LevelView& L, const ColourSet& cs) {
   int tj_shift = -1; for (int q = 0; q < 12; ++q) if ((1 << q) == TJ) tj_shift = q;
   if (minb == 2) launch_A4_nz<2>(st, L, cs, grid, 2 * smem1, TI, TJ, ntj, ntiles, tj_shift);
   else launch_A4_nz<3>(st, L, cs, grid, 2 * smem1, TI, TJ, ntj, ntiles, tj_shift);
-  ++g_launches;
 }
 
 // Kernel B: the sequential part of the red-black bottom coupling, on the 2-D k=1 plane only.
@@ -666,11 +674,10 @@ void launch_relax_B(cudaStream_t st, const LevelView& L, const ColourSet& cs) {
   while (D > 2 && (size_t)(2 + 5 * D) * ny2 * sizeof(double) > 200 * 1024) D /= 2;
   const size_t smem = (size_t)(2 + 5 * D) * ny2 * sizeof(double);
   const int nchunks = (L.nx + L.rb_chunk - 1) / L.rb_chunk;
-  if (threads == 32 && D == 8) k_relax_B<8, true><<<nchunks, 32, smem, st>>>(L, cs);
-  else if (D == 8) k_relax_B<8, false><<<nchunks, threads, smem, st>>>(L, cs);
-  else if (D == 4) k_relax_B<4, false><<<nchunks, threads, smem, st>>>(L, cs);
-  else k_relax_B<2, false><<<nchunks, threads, smem, st>>>(L, cs);
-  ++g_launches;
+  if (threads == 32 && D == 8) launch_k(k_relax_B<8, true>, nchunks, 32, smem, st, L, cs);
+  else if (D == 8) launch_k(k_relax_B<8, false>, nchunks, threads, smem, st, L, cs);
+  else if (D == 4) launch_k(k_relax_B<4, false>, nchunks, threads, smem, st, L, cs);
+  else launch_k(k_relax_B<2, false>, nchunks, threads, smem, st, L, cs);
 }
 
 // Kernel C: p(:,j,i) += s(j,i) * g(:,j,i) on the columns of the colour
@@ -713,37 +720,51 @@ __global__ void __launch_bounds__(256) k_relax_C(LevelView L, ColourSet cs, int 
 // entirely in shared memory, then streams p += s g over its rows with the Neumann mirrors.  The k=1 plane is double
 // buffered (x1old is read, x1new is written completely) because other CTAs still need the old values.
 // Saves the B launch and its serial latency on every colour.
-__global__ void __launch_bounds__(256) k_relax_BC(LevelView L, ColourSet cs, const double* __restrict__ x1old, double* __restrict__ x1new, int TJ) {
-  extern __shared__ __align__(16) double sm[];
+// CG: read everything another CTA of the same launch may have written (x1old, q1, p) with ld.global.cg -- used by the
+// cooperative mid-level kernel, where the L1s are not coherent; the stand-alone kernel reads them the plain way.
+template <bool CG> __device__ __forceinline__ double ld_shared_data(const double* q) { return CG ? __ldcg(q) : *q; }
+template <bool CG>
+__device__ __forceinline__ void bc_block(const LevelView& L, int rb, const double* __restrict__ x1old, double* __restrict__ x1new, int TJ,
+                                         int bx, int by, double* sm) {
   const int nx = L.nx, ny = L.ny, ny2 = ny + 2, nz = L.nz;
-  const int c0 = 1 + blockIdx.y * L.rb_chunk, c1 = min(nx, c0 + L.rb_chunk - 1), i0 = max(1, c0 - L.rb_W);
+  const int c0 = 1 + by * L.rb_chunk, c1 = min(nx, c0 + L.rb_chunk - 1), i0 = max(1, c0 - L.rb_W);
   const int E = c1 - i0;
-  const int jA = 2 * blockIdx.x * TJ + 1, jB = min(ny, jA + 2 * TJ - 1);
+  const int jA = 2 * bx * TJ + 1, jB = min(ny, jA + 2 * TJ - 1);
   const int wlo = max(0, jA - 1 - E), whi = min(ny + 1, jB + 1 + E);
   const int width = whi - wlo + 1, pitch = 2 * TJ + 2 * (L.rb_chunk + L.rb_W) + 4;
   double* rowA = sm + 1; double* rowB = sm + pitch + 1;      // index [j - wlo], one pad cell on each side
   double* sblk = sm + 2 * pitch;                             // [row - c0][j - jA]
-  for (int t = threadIdx.x; t < width; t += blockDim.x) rowA[t] = x1old[(size_t)(wlo + t) + (size_t)ny2 * (i0 - 1)];
+  // operands of all trapezoid rows, [i - i0][j - wlo]: fetched in one L2 round trip instead of one per (serial) row
+  double* sq = sblk + L.rb_chunk * 2 * TJ; double* s5 = sq + (E + 1) * pitch; double* s8 = s5 + (E + 1) * pitch; double* sg = s8 + (E + 1) * pitch;
+  for (int t = threadIdx.x; t < (E + 1) * width; t += blockDim.x) {
+    const int r = t / width, jj = t - r * width;
+    const size_t c = (size_t)(wlo + jj) + (size_t)ny2 * (i0 + r);
+    sq[r * pitch + jj] = ld_shared_data<CG>(L.q1 + c); s5[r * pitch + jj] = L.c5b[c]; s8[r * pitch + jj] = L.c8b[c]; sg[r * pitch + jj] = L.g1[c];
+  }
+  double* sh0 = sg + (E + 1) * pitch; double* shN = sh0 + (E + 1);       // x1old(0, i) and x1old(ny+1, i) of the trapezoid rows
+  for (int t = threadIdx.x; t < 2 * (E + 1); t += blockDim.x) {
+    const int r = t >> 1;
+    if (t & 1) { if (whi == ny + 1) shN[r] = ld_shared_data<CG>(x1old + (size_t)(ny + 1) + (size_t)ny2 * (i0 + r)); }
+    else if (wlo == 0) sh0[r] = ld_shared_data<CG>(x1old + (size_t)ny2 * (i0 + r));
+  }
+  for (int t = threadIdx.x; t < width; t += blockDim.x) rowA[t] = ld_shared_data<CG>(x1old + (size_t)(wlo + t) + (size_t)ny2 * (i0 - 1));
   if (threadIdx.x == 0) { rowA[-1] = 0.0; rowA[width] = 0.0; rowB[-1] = 0.0; rowB[width] = 0.0; }
   double* prev = rowA; double* cur = rowB;
   // this thread's entry of a step: the t-th column of the step's parity inside [max(1,wlo+1), min(ny,whi-1)]
   const int lo = max(1, wlo + 1), hi = min(ny, whi - 1);
-  auto my_j = [&](int i) { const int js = 1 + ((i + cs.rb) & 1); int j = lo + (((lo ^ js) & 1) ? 1 : 0) + 2 * (int)threadIdx.x; return j; };
-  double o5 = 0, o8 = 0, oq = 0, og = 0;
-  { const int j = my_j(i0); if (j <= hi) { const size_t c = (size_t)j + (size_t)ny2 * i0; o5 = L.c5b[c]; o8 = L.c8b[c]; oq = L.q1[c]; og = L.g1[c]; } }
+  auto my_j = [&](int i) { const int js = 1 + ((i + rb) & 1); int j = lo + (((lo ^ js) & 1) ? 1 : 0) + 2 * (int)threadIdx.x; return j; };
   __syncthreads();
   for (int i = i0; i <= c1; ++i) {
     const int j = my_j(i);
-    const double a5 = o5, a8 = o8, aq = oq, ag = og;
-    if (i < c1) { const int jn = my_j(i + 1); if (jn <= hi) { const size_t c = (size_t)jn + (size_t)ny2 * (i + 1); o5 = L.c5b[c]; o8 = L.c8b[c]; oq = L.q1[c]; og = L.g1[c]; } }
     if (j <= hi) {
-      const double sv = -(a5 * prev[j + 1 - wlo] + a8 * prev[j - 1 - wlo]);
-      cur[j - wlo] = aq + sv * ag;
+      const int o = (i - i0) * pitch + (j - wlo);
+      const double sv = -(s5[o] * prev[j + 1 - wlo] + s8[o] * prev[j - 1 - wlo]);
+      cur[j - wlo] = sq[o] + sv * sg[o];
       if (i >= c0 && j >= jA && j <= jB) sblk[(i - c0) * 2 * TJ + (j - jA)] = sv;
     }
     if (threadIdx.x == 0) {
-      if (wlo == 0) cur[0] = x1old[(size_t)ny2 * i];
-      if (whi == ny + 1) cur[ny + 1 - wlo] = x1old[(size_t)(ny + 1) + (size_t)ny2 * i];
+      if (wlo == 0) cur[0] = sh0[i - i0];
+      if (whi == ny + 1) cur[ny + 1 - wlo] = shN[i - i0];
     }
     __syncthreads();
     double* tmp = prev; prev = cur; cur = tmp;
@@ -756,35 +777,39 @@ __global__ void __launch_bounds__(256) k_relax_BC(LevelView L, ColourSet cs, con
   for (int e = threadIdx.x; e < nelem; e += blockDim.x) {
     const int k = e % nz; int t = e / nz; const int cj = t % ncols, r = t / ncols;
     const int i = c0 + r;
-    const int js = 1 + ((i + cs.rb) & 1);
+    const int js = 1 + ((i + rb) & 1);
     const int j = jA + (js - 1) + 2 * cj;
     if (j > jB) continue;
     const double sv = sblk[r * 2 * TJ + (j - jA)];
     const size_t idx = IDX3(k, j, i, nz, ny2);
-    const double v = L.p[idx] + sv * L.g[idx];
+    const double v = ld_shared_data<CG>(L.p + idx) + sv * L.g[idx];
     store_mirrored(L.p, idx, v, j, i, ny, nx, sj, si, true);
     if (k == 0) {
       const size_t c2d = (size_t)j + (size_t)ny2 * i;
       store_mirrored(x1new, c2d, v, j, i, ny, nx, 1, (size_t)ny2, true);
       const int jp = (js == 1) ? j + 1 : j - 1;                               // the other-colour cell of the pair keeps its value
-      if (jp >= 1 && jp <= ny) store_mirrored(x1new, (size_t)jp + (size_t)ny2 * i, x1old[(size_t)jp + (size_t)ny2 * i], jp, i, ny, nx, 1, (size_t)ny2, true);
+      if (jp >= 1 && jp <= ny) store_mirrored(x1new, (size_t)jp + (size_t)ny2 * i, ld_shared_data<CG>(x1old + (size_t)jp + (size_t)ny2 * i), jp, i, ny, nx, 1, (size_t)ny2, true);
     }
   }
+}
+__global__ void __launch_bounds__(256) k_relax_BC(LevelView L, ColourSet cs, const double* __restrict__ x1old, double* __restrict__ x1new, int TJ) {
+  extern __shared__ __align__(16) double sm[];
+  bc_block<false>(L, cs.rb, x1old, x1new, TJ, blockIdx.x, blockIdx.y, sm);
 }
 void launch_relax_BC(cudaStream_t st, const LevelView& L, const ColourSet& cs, const double* x1old, double* x1new) {
   const int nyc = (L.ny + 1) / 2;
   const int TJ = nyc < 8 ? nyc : 8;          // narrow blocks: many CTAs, the trapezoid overhead is 2-D only
   const int ntj = (nyc + TJ - 1) / TJ, nchunks = (L.nx + L.rb_chunk - 1) / L.rb_chunk;
   const int pitch = 2 * TJ + 2 * (L.rb_chunk + L.rb_W) + 4;
-  const size_t smem = ((size_t)2 * pitch + (size_t)L.rb_chunk * 2 * TJ) * sizeof(double);
+  const size_t smem = ((size_t)2 * pitch + (size_t)L.rb_chunk * 2 * TJ + (size_t)(L.rb_chunk + L.rb_W) * (4 * pitch + 2)) * sizeof(double);
   dim3 grid(ntj, nchunks);
-  k_relax_BC<<<grid, 256, smem, st>>>(L, cs, x1old, x1new, TJ); ++g_launches;
+  launch_k(k_relax_BC, grid, 256, smem, st, L, cs, x1old, x1new, TJ);
 }
 void launch_relax_C(cudaStream_t st, const LevelView& L, const ColourSet& cs) {
   const int nyc = (L.ny + 1) / 2;
   const int nvi = (L.nx - cs.istart) / cs.istep + 1;
   dim3 grid(blocks_for((size_t)nyc * L.nz, 1024), nvi);
-  k_relax_C<<<grid, 256, 0, st>>>(L, cs, nyc); ++g_launches;
+  launch_k(k_relax_C, grid, 256, 0, st, L, cs, nyc);
 }
 
 // Fused relaxation of a SMALL level: all `nsweeps` red-black sweeps (both colours, bottom-coupling recurrence,
@@ -925,8 +950,184 @@ __global__ void __launch_bounds__(1024) k_relax_small(LevelView L, int nsweeps, 
   }
   if (all_smem) for (int e = threadIdx.x; e < n3; e += blockDim.x) L.p[e] = p[e];
 }
+// Fused relaxation of a MID-SIZE level without lateral neighbour ranks: all `nsweeps` red-black sweeps in ONE cooperative
+// launch of G co-resident CTAs that meet at software grid barriers (an atomic counter in L2) between the phases
+// A (column solves) -> B (chunked bottom recurrence) -> C (rank-1 update + Neumann mirrors) of every colour.
+// These levels (10^4 .. 10^6 points) are launch-latency bound: a colour costs three ~1 us barriers here instead of two or
+// three dependent launches of ~6 us.  Same arithmetic, operation by operation, as kernels A4 / B / C.
+// Values written by other CTAs during the launch (p, q1, s, x1) are always read with ld.global.cg (L2): the L1s are not
+// coherent inside a launch.  Coefficients are read-only and stay L1-resident across sweeps (a CTA keeps its columns).
+//   bar[0]: barrier counter, bar[1]: exit counter (the last CTA to leave zeroes both for the next launch)
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
+  unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+template <int NZ>
+__global__ void __launch_bounds__(512, 1) k_relax_mid(LevelView L, int nsweeps, int rank1, int TC, unsigned* __restrict__ bar) {
+  extern __shared__ __align__(16) double sm[];
+  const int nx = L.nx, ny = L.ny, ny2 = ny + 2, nyc = ny / 2, pitch = NZ + 1;
+  constexpr int sj = NZ; const int si = NZ * ny2;
+  const int G = gridDim.x;
+  const int ncol = nx * nyc;                                  // columns of one colour; column c -> row i = 1 + c / nyc
+  const int ntiles = (ncol + TC - 1) / TC;
+  double* s_rhs = sm; double* s_bet = sm + TC * pitch; double* s_ud = s_bet + TC * pitch;
+  unsigned target = 0;
+  auto gbar = [&]() {
+    target += G;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");   // release: the CTA's stores (ordered by bar.sync) are out
+      while (ld_acquire_gpu_u32(bar) < target) { }
+    }
+    __syncthreads();
+  };
+  const double* __restrict__ b = L.b; const double* __restrict__ bet = L.bet; const double* __restrict__ g = L.g;
+  const double* __restrict__ c2 = L.cA[1]; const double* __restrict__ c3 = L.cA[2]; const double* __restrict__ c4 = L.cA[3];
+  const double* __restrict__ c5 = L.cA[4]; const double* __restrict__ c6 = L.cA[5]; const double* __restrict__ c7 = L.cA[6];
+  const double* __restrict__ c8 = L.cA[7];
+  double* p = L.p;
+  double* x1cur = L.x1; double* x1alt = L.x1b;
+  if (rank1) {   // x1 = p(1,:,:) on the whole plane incl. the halo; afterwards every colour writes the next k=1 plane completely
+    const int n2 = ny2 * (nx + 2);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n2; e += G * blockDim.x) x1cur[e] = __ldcg(p + (size_t)e * NZ);
+    gbar();
+  }
+#ifdef MGB_MID_TIMING
+  long long tA = 0, tB1 = 0, tBC = 0, tB2 = 0, t0;
+#define MID_T(acc) { const long long t1 = clock64(); acc += t1 - t0; t0 = t1; }
+  t0 = clock64();
+#else
+#define MID_T(acc)
+#endif
+  for (int it = 0; it < nsweeps; ++it) for (int rb = 1; rb <= 2; ++rb) {
+    // ---- A: tiles of TC columns; rhs by (k, column) threads, Thomas by one thread per column, coalesced write-back
+    for (int tile = blockIdx.x; tile < ntiles; tile += G) {
+      const int cbase = tile * TC, tcn = min(TC, ncol - cbase);
+      for (int e = threadIdx.x; e < tcn * NZ; e += blockDim.x) {
+        const int k = e & (NZ - 1), cl = e / NZ, c = cbase + cl;
+        const int i = 1 + c / nyc, jc = c - (i - 1) * nyc;
+        const int j = 1 + ((i + rb) & 1) + 2 * jc;
+        const int idx = k + NZ * (j + ny2 * i);
+        const int im = idx - si, ip = idx + si;
+        const double bb = b[idx], bt = bet[idx], udv = c2[idx + 1];
+        const double a3 = c3[idx],           q3 = __ldcg(p + idx - sj + 1);
+        const double a3n = c3[idx + sj - 1], q3n = __ldcg(p + idx + sj - 1);
+        const double a4 = c4[idx],           q4 = __ldcg(p + idx - sj);
+        const double a4n = c4[idx + sj],     q4n = __ldcg(p + idx + sj);
+        const double a5 = c5[idx],           q5 = __ldcg(p + idx - sj - 1);
+        const double a5n = c5[idx + sj + 1], q5n = __ldcg(p + idx + sj + 1);
+        const double a6 = c6[idx],           q6 = __ldcg(p + im + 1);
+        const double a6n = c6[ip - 1],       q6n = __ldcg(p + ip - 1);
+        const double a7 = c7[idx],           q7 = __ldcg(p + im);
+        const double a7n = c7[ip],           q7n = __ldcg(p + ip);
+        const double a8 = c8[idx],           q8 = __ldcg(p + im - 1);
+        const double a8n = c8[ip + 1],       q8n = __ldcg(p + ip + 1);
+        const bool lo = (k > 0), hi = (k < NZ - 1);
+        double acc = bb;
+        if (hi) acc = acc - a3 * q3;
+        if (lo) acc = acc - a3n * q3n;
+        acc = acc - a4 * q4;
+        acc = acc - a4n * q4n;
+        if (lo) acc = acc - a5 * q5;
+        if (hi) acc = acc - a5n * q5n;
+        if (hi) acc = acc - a6 * q6;
+        if (lo) acc = acc - a6n * q6n;
+        acc = acc - a7 * q7;
+        acc = acc - a7n * q7n;
+        if (lo) acc = acc - a8 * q8;
+        if (hi) acc = acc - a8n * q8n;
+        if (k == 0 && rank1) {
+          const int c2d = j + ny2 * i;
+          acc = acc - L.c5b[c2d - 1 + ny2] * __ldcg(x1cur + c2d - 1 + ny2);
+          acc = acc - L.c8b[c2d + 1 + ny2] * __ldcg(x1cur + c2d + 1 + ny2);
+        }
+        const int so = cl * pitch + k;
+        s_rhs[so] = acc; s_bet[so] = bt; s_ud[so] = hi ? udv : 0.0;
+      }
+      __syncthreads();
+      for (int cl = threadIdx.x; cl < tcn; cl += blockDim.x) {
+        double* x = s_rhs + cl * pitch; const double* bt = s_bet + cl * pitch; const double* ud = s_ud + cl * pitch;
+        double xm = x[0] * bt[0];
+        x[0] = xm;
+#pragma unroll
+        for (int k = 1; k < NZ; ++k) { xm = (x[k] - ud[k - 1] * xm) * bt[k]; x[k] = xm; }
+#pragma unroll
+        for (int k = NZ - 2; k >= 0; --k) { xm = x[k] - (ud[k] * bt[k]) * xm; x[k] = xm; }
+        if (rank1) { const int c = cbase + cl; const int i = 1 + c / nyc, jc = c - (i - 1) * nyc; L.q1[1 + ((i + rb) & 1) + 2 * jc + ny2 * i] = xm; }
+      }
+      __syncthreads();
+      for (int e = threadIdx.x; e < tcn * NZ; e += blockDim.x) {
+        const int k = e & (NZ - 1), cl = e / NZ, c = cbase + cl;
+        const int i = 1 + c / nyc, jc = c - (i - 1) * nyc;
+        const int j = 1 + ((i + rb) & 1) + 2 * jc;
+        const int idx = k + NZ * (j + ny2 * i);
+        const double v = s_rhs[cl * pitch + k];
+        if (rank1) p[idx] = v;                               // q only; final after C
+        else store_mirrored(p, (size_t)idx, v, j, i, ny, nx, (size_t)sj, (size_t)si, true);
+      }
+      __syncthreads();
+    }
+    MID_T(tA)
+    gbar();
+    MID_T(tB1)
+    if (rank1) {
+      // ---- B + C fused per (chunk, block of 2*TJ columns) task, exactly as k_relax_BC: trapezoid recurrence in shared memory,
+      //      then p += s g with the Neumann mirrors; the k=1 plane is double buffered (other tasks still read the old one)
+      const int TJ = nyc < 8 ? nyc : 8, ntj = (nyc + TJ - 1) / TJ, nchunks = (nx + L.rb_chunk - 1) / L.rb_chunk;
+      for (int task = blockIdx.x; task < ntj * nchunks; task += G) {
+        bc_block<true>(L, rb, x1cur, x1alt, TJ, task % ntj, task / ntj, sm);
+        __syncthreads();
+      }
+      { double* t = x1cur; x1cur = x1alt; x1alt = t; }
+      MID_T(tBC)
+      gbar();
+      MID_T(tB2)
+    }
+  }
+#ifdef MGB_MID_TIMING
+  if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == G - 1))
+    printf("mid nz=%d nx=%d G=%d cta=%d W=%d: per colour cycles A=%lld bar1=%lld BC=%lld bar2=%lld\n", NZ, nx, G, (int)blockIdx.x, L.rb_W,
+           tA / (2 * nsweeps), tB1 / (2 * nsweeps), tBC / (2 * nsweeps), tB2 / (2 * nsweeps));
+#endif
+  // leave the counters zeroed for the next launch: the last CTA out does it
+  __syncthreads();
+  if (threadIdx.x == 0) { __threadfence(); if (atomicAdd(bar + 1, 1u) == (unsigned)G - 1) { bar[0] = 0; bar[1] = 0; } }
+}
+static int mid_tc(const LevelView& L) { (void)L; return 64; }
+bool relax_mid_supported(const LevelView& L) {
+  const bool nz_ok = (L.nz == 2 || L.nz == 4 || L.nz == 8 || L.nz == 16 || L.nz == 32);
+  const size_t n3 = (size_t)L.nz * (L.ny + 2) * (L.nx + 2);
+  return nz_ok && (L.ny % 2 == 0) && n3 <= (size_t)1500000 && L.rb_W <= RB_WMAX;   // chunked recurrence only
+}
+void launch_relax_mid(cudaStream_t st, const LevelView& L, int nsweeps, int rank1, unsigned* bar) {
+  const int TC = mid_tc(L);
+  const int ncol = L.nx * (L.ny / 2), ntiles = (ncol + TC - 1) / TC;
+  const int G = ntiles < 148 ? ntiles : 148;
+  const int nyc = L.ny / 2, TJ = nyc < 8 ? nyc : 8;
+  const size_t bc_pitch = (size_t)2 * TJ + 2 * (L.rb_chunk + L.rb_W) + 4;
+  const size_t bc_doubles = 2 * bc_pitch + (size_t)L.rb_chunk * 2 * TJ + (size_t)(L.rb_chunk + L.rb_W) * (4 * bc_pitch + 2);
+  const size_t a_doubles = (size_t)3 * TC * (L.nz + 1);
+  const size_t smem = (a_doubles > bc_doubles ? a_doubles : bc_doubles) * sizeof(double);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(G); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;   // co-residency is required (grid barriers)
+  cfg.attrs = at; cfg.numAttrs = 1;
+  switch (L.nz) {
+    case 2: cudaLaunchKernelEx(&cfg, k_relax_mid<2>, L, nsweeps, rank1, TC, bar); break;
+    case 4: cudaLaunchKernelEx(&cfg, k_relax_mid<4>, L, nsweeps, rank1, TC, bar); break;
+    case 8: cudaLaunchKernelEx(&cfg, k_relax_mid<8>, L, nsweeps, rank1, TC, bar); break;
+    case 16: cudaLaunchKernelEx(&cfg, k_relax_mid<16>, L, nsweeps, rank1, TC, bar); break;
+    default: cudaLaunchKernelEx(&cfg, k_relax_mid<32>, L, nsweeps, rank1, TC, bar); break;
+  }
+  ++g_launches;
+}
 void kernels_init() {
   a4_attrs<2>(); a4_attrs<3>();
+  cudaFuncSetAttribute(k_relax_BC, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_relax_mid<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_relax_mid<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_relax_mid<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_relax_mid<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_relax_mid<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_relax_B<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   cudaFuncSetAttribute(k_relax_B<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   cudaFuncSetAttribute(k_relax_B<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
@@ -940,7 +1141,9 @@ bool relax_small_supported(const LevelView& L) {
   const size_t n2 = (size_t)(L.ny + 2) * (L.nx + 2);
   const bool nz_ok = (L.nz == 2 || L.nz == 4 || L.nz == 8 || L.nz == 16);
   // single-CTA relaxation pays off on tiny levels only; a 2-level (nz = 2) grid may be a little wider (coarsest level of a multi-GPU job)
-  return nz_ok && (L.ny % 2 == 0) && (n2 <= (size_t)34 * 34 || (L.nz == 2 && n2 <= (size_t)66 * 34));
+  static const bool no_mid = []() { const char* e = std::getenv("MGB_NO_MID_KERNEL"); return e && e[0] == '1'; }();
+  if (no_mid) return nz_ok && (L.ny % 2 == 0) && (n2 <= (size_t)34 * 34 || (L.nz == 2 && n2 <= (size_t)66 * 34));
+  return nz_ok && (L.ny % 2 == 0) && n2 <= (size_t)18 * 18;       // larger levels: the cooperative multi-CTA kernel
 }
 void launch_relax_small(cudaStream_t st, const LevelView& L, int nsweeps, int rank1) {
   const size_t n2 = (size_t)(L.ny + 2) * (L.nx + 2);
@@ -951,12 +1154,11 @@ void launch_relax_small(cudaStream_t st, const LevelView& L, int nsweeps, int ra
   int threads = 64; const int ncol = L.nx * (L.ny / 2);
   while (threads < ncol && threads < 1024) threads *= 2;
   switch (L.nz) {
-    case 2: k_relax_small<2><<<1, threads, smem, st>>>(L, nsweeps, rank1, all_smem); break;
-    case 4: k_relax_small<4><<<1, threads, smem, st>>>(L, nsweeps, rank1, all_smem); break;
-    case 8: k_relax_small<8><<<1, threads, smem, st>>>(L, nsweeps, rank1, all_smem); break;
-    default: k_relax_small<16><<<1, threads, smem, st>>>(L, nsweeps, rank1, all_smem); break;
+    case 2: launch_k(k_relax_small<2>, 1, threads, smem, st, L, nsweeps, rank1, all_smem); break;
+    case 4: launch_k(k_relax_small<4>, 1, threads, smem, st, L, nsweeps, rank1, all_smem); break;
+    case 8: launch_k(k_relax_small<8>, 1, threads, smem, st, L, nsweeps, rank1, all_smem); break;
+    default: launch_k(k_relax_small<16>, 1, threads, smem, st, L, nsweeps, rank1, all_smem); break;
   }
-  ++g_launches;
 }
 
 // =====================================================================================================
@@ -1057,14 +1259,13 @@ int residual_num_partials(const LevelView& L) { return L.nx * residual_chunks(L)
 void launch_residual(cudaStream_t st, const LevelView& L, int real_matrix, double* partials, double* sum_out) {
   const int chunks = residual_chunks(L);
   switch (L.nz) {
-    case 128: k_residual<128><<<L.nx * chunks, 256, 0, st>>>(L, real_matrix, chunks, partials); break;
-    case 64: k_residual<64><<<L.nx * chunks, 256, 0, st>>>(L, real_matrix, chunks, partials); break;
-    case 32: k_residual<32><<<L.nx * chunks, 256, 0, st>>>(L, real_matrix, chunks, partials); break;
-    case 16: k_residual<16><<<L.nx * chunks, 256, 0, st>>>(L, real_matrix, chunks, partials); break;
-    default: k_residual<0><<<L.nx * chunks, 256, 0, st>>>(L, real_matrix, chunks, partials); break;
+    case 128: launch_k(k_residual<128>, L.nx * chunks, 256, 0, st, L, real_matrix, chunks, partials); break;
+    case 64: launch_k(k_residual<64>, L.nx * chunks, 256, 0, st, L, real_matrix, chunks, partials); break;
+    case 32: launch_k(k_residual<32>, L.nx * chunks, 256, 0, st, L, real_matrix, chunks, partials); break;
+    case 16: launch_k(k_residual<16>, L.nx * chunks, 256, 0, st, L, real_matrix, chunks, partials); break;
+    default: launch_k(k_residual<0>, L.nx * chunks, 256, 0, st, L, real_matrix, chunks, partials); break;
   }
-  ++g_launches;
-  k_reduce_final<<<1, 256, 0, st>>>(partials, L.nx * chunks, sum_out); ++g_launches;
+  launch_k(k_reduce_final, 1, 256, 0, st, partials, L.nx * chunks, sum_out);
 }
 __global__ void __launch_bounds__(256) k_sumsq(const double* __restrict__ a, int nz, int ny, int chunks_per_i, double* __restrict__ partials) {
   __shared__ double s_red[8];
@@ -1080,8 +1281,8 @@ __global__ void __launch_bounds__(256) k_sumsq(const double* __restrict__ a, int
 }
 void launch_sumsq(cudaStream_t st, const LevelView& L, const double* a, double* partials, double* sum_out) {
   const int chunks = residual_chunks(L);
-  k_sumsq<<<L.nx * chunks, 256, 0, st>>>(a, L.nz, L.ny, chunks, partials); ++g_launches;
-  k_reduce_final<<<1, 256, 0, st>>>(partials, L.nx * chunks, sum_out); ++g_launches;
+  launch_k(k_sumsq, L.nx * chunks, 256, 0, st, a, L.nz, L.ny, chunks, partials);
+  launch_k(k_reduce_final, 1, 256, 0, st, partials, L.nx * chunks, sum_out);
 }
 
 // =====================================================================================================
@@ -1089,24 +1290,26 @@ void launch_sumsq(cudaStream_t st, const LevelView& L, const double* a, double* 
 // =====================================================================================================
 // restriction: y(k2,j2,i2) = sum of the 8 fine cells (src/mg_intergrids.f90:149-160), same summation order
 __global__ void __launch_bounds__(256) k_restrict8(const double* __restrict__ xf, int nzf, int nyf, double* __restrict__ yc, int nzc, int nyc, int nxc) {
-  const size_t n = (size_t)nzc * nyc * nxc;
-  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = nzc * nyc * nxc;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
-  const int k2 = (int)(e % nzc); size_t t = e / nzc; const int j2 = 1 + (int)(t % nyc), i2 = 1 + (int)(t / nyc);
+  const int t = e / nzc, k2 = e - t * nzc;
+  const int i2 = 1 + t / nyc, j2 = 1 + (t - (i2 - 1) * nyc);
   const int k = 2 * k2, j = 2 * j2 - 1, i = 2 * i2 - 1;       // k 0-based
   const int nyf2 = nyf + 2;
-  const size_t f00 = IDX3(k, j, i, nzf, nyf2), sj = nzf, si = (size_t)nzf * nyf2;
+  const int sj = nzf, si = nzf * nyf2;
+  const int f00 = k + nzf * (j + nyf2 * i);
   const double2 a = *reinterpret_cast<const double2*>(xf + f00);             // (k, k+1) at (j, i)
   const double2 b = *reinterpret_cast<const double2*>(xf + f00 + si);        // (j, i+1)
   const double2 c = *reinterpret_cast<const double2*>(xf + f00 + sj);        // (j+1, i)
   const double2 d = *reinterpret_cast<const double2*>(xf + f00 + sj + si);   // (j+1, i+1)
   double z = a.x + b.x + c.x + d.x + a.y + b.y + c.y + d.y;
-  yc[IDX3(k2, j2, i2, nzc, nyc + 2)] = z;
+  yc[k2 + nzc * (j2 + (nyc + 2) * i2)] = z;
 }
 void launch_restrict8(cudaStream_t st, const double* xf, int nzf, int nyf, int nxf, double* yc, int nzc, int nyc, int nxc) {
   (void)nxf;
   size_t n = (size_t)nzc * nyc * nxc;
-  k_restrict8<<<blocks_for(n, 256), 256, 0, st>>>(xf, nzf, nyf, yc, nzc, nyc, nxc); ++g_launches;
+  launch_k(k_restrict8, blocks_for(n, 256), 256, 0, st, xf, nzf, nyf, yc, nzc, nyc, nxc);
 }
 
 // prolongation (src/mg_intergrids.f90:366-450 linear, :336-363 nearest); thread per fine interior point
@@ -1149,54 +1352,67 @@ __global__ void __launch_bounds__(256) k_prolong(const double* __restrict__ xc, 
 // per 8 fine points instead of 64, and 16-byte coalesced read-modify-write of p.
 __global__ void __launch_bounds__(256, 3) k_prolong8(const double* __restrict__ xc, int nzc, int nyc, int nxc,
                                                  double* __restrict__ rf, double* __restrict__ pf, int mode) {
-  const size_t n = (size_t)nzc * nyc * nxc;
-  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n) return;
-  const int k2 = 1 + (int)(e % nzc); size_t t = e / nzc; const int j2 = 1 + (int)(t % nyc), i2 = 1 + (int)(t / nyc);   // Fortran indices
+  const int n = nzc * nyc * nxc;                                              // 32-bit element indices throughout
+  const int e_raw = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = e_raw < n;
+  const int e = valid ? e_raw : n - 1;                                        // idle lanes still take part in the shuffles
+  const int lane = threadIdx.x & 31;
+  const int t = e / nzc, k2 = 1 + (e - t * nzc);
+  const int i2 = 1 + t / nyc, j2 = 1 + (t - (i2 - 1) * nyc);                  // Fortran indices
   const int nyc2 = nyc + 2, nzf = 2 * nzc, nyf2 = 2 * nyc + 2;
   const double a = 9.0 / 16.0, b = 3.0 / 16.0, c = 1.0 / 16.0, d = 27.0 / 64.0, ee = 9.0 / 64.0, f = 3.0 / 64.0, g = 1.0 / 64.0;
-  const int km = (k2 > 1) ? k2 - 1 : k2, kp = (k2 < nzc) ? k2 + 1 : k2;      // clamped (unused values at the ends)
   // the four fine (k,k+1) pairs of p are the only DRAM reads: issue them first so they fly during the coarse loads
-  size_t of[4]; double2 pv[4];
+  int of[4]; double2 pv[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int jf = 2 * j2 - 1 + (q >> 1), i_f = 2 * i2 - 1 + (q & 1);
-    of[q] = (size_t)(2 * (k2 - 1)) + (size_t)nzf * ((size_t)jf + (size_t)nyf2 * (size_t)i_f);
+    of[q] = 2 * (k2 - 1) + nzf * (jf + nyf2 * i_f);
     pv[q] = (mode == 0) ? make_double2(0.0, 0.0) : *reinterpret_cast<const double2*>(pf + of[q]);
   }
-  double X[3][3][3];                                                           // [level: km,k2,kp][dj+1][di+1]
+  // coarse value at (k2, j2+dj, i2+di) and its vertical neighbours: the levels k2-1 / k2+1 of the same column sit in the
+  // adjacent lanes (k2 is the fastest index), so they travel by shuffle; only a warp-boundary lane loads them
+  const bool need_lo = (lane == 0) && (k2 > 1), need_hi = (lane == 31) && (k2 < nzc);
+  auto ld3 = [&](int dj, int di, double& xm, double& x0, double& xp) {
+    const int o = nzc * ((j2 + dj) + nyc2 * (i2 + di)) + k2 - 1;
+    x0 = xc[o];
+    xm = __shfl_up_sync(0xffffffffu, x0, 1); xp = __shfl_down_sync(0xffffffffu, x0, 1);
+    if (need_lo) xm = xc[o - 1];
+    if (need_hi) xp = xc[o + 1];
+  };
+  double Cm[3], C0[3], Cp[3];                                                  // centre row (dj = 0), di = -1, 0, +1
 #pragma unroll
-  for (int dj = -1; dj <= 1; ++dj)
+  for (int di = -1; di <= 1; ++di) ld3(0, di, Cm[di + 1], C0[di + 1], Cp[di + 1]);
 #pragma unroll
-    for (int di = -1; di <= 1; ++di) {
-      const size_t o = (size_t)nzc * ((size_t)(j2 + dj) + (size_t)nyc2 * (size_t)(i2 + di));
-      X[0][dj + 1][di + 1] = xc[o + km - 1]; X[1][dj + 1][di + 1] = xc[o + k2 - 1]; X[2][dj + 1][di + 1] = xc[o + kp - 1];
-    }
+  for (int cj = 0; cj < 2; ++cj) {
+    const int dj = cj ? +1 : -1;
+    double Sm[3], S0[3], Sp[3];                                                // side row (dj), di = -1, 0, +1
 #pragma unroll
-  for (int cj = 0; cj < 2; ++cj)
+    for (int di = -1; di <= 1; ++di) ld3(dj, di, Sm[di + 1], S0[di + 1], Sp[di + 1]);
 #pragma unroll
     for (int ci = 0; ci < 2; ++ci) {
-      const int dj = cj ? +1 : -1, di = ci ? +1 : -1, q = cj * 2 + ci;
-      const double x00 = X[1][1][1], xdd = X[1][dj + 1][di + 1], xd0 = X[1][dj + 1][1], x0d = X[1][1][di + 1];
+      const int di = ci ? +1 : -1, q = cj * 2 + ci;
+      const double x00 = C0[1], xdd = S0[di + 1], xd0 = S0[1], x0d = C0[di + 1];
       double vlo, vhi;
       if (k2 == 1) vlo = a * x00 + c * xdd + b * xd0 + b * x0d;                                  // fine K = 1
-      else { const double y00 = X[0][1][1], ydd = X[0][dj + 1][di + 1], yd0 = X[0][dj + 1][1], y0d = X[0][1][di + 1];
+      else { const double y00 = Cm[1], ydd = Sm[di + 1], yd0 = Sm[1], y0d = Cm[di + 1];
              vlo = d * x00 + f * xdd + ee * xd0 + ee * x0d + ee * y00 + g * ydd + f * yd0 + f * y0d; }
       if (k2 == nzc) { vhi = a * x00 + c * xdd + b * xd0 + b * x0d; vhi = 0.5 * vhi; }            // fine K = nzf
-      else { const double y00 = X[2][1][1], ydd = X[2][dj + 1][di + 1], yd0 = X[2][dj + 1][1], y0d = X[2][1][di + 1];
+      else { const double y00 = Cp[1], ydd = Sp[di + 1], yd0 = Sp[1], y0d = Cp[di + 1];
              vhi = d * x00 + f * xdd + ee * xd0 + ee * x0d + ee * y00 + g * ydd + f * yd0 + f * y0d; }
+      if (!valid) continue;
       if (mode == 0) *reinterpret_cast<double2*>(rf + of[q]) = make_double2(vlo, vhi);
       else *reinterpret_cast<double2*>(pf + of[q]) = make_double2(pv[q].x + vlo, pv[q].y + vhi);
     }
+  }
 }
 void launch_prolong(cudaStream_t st, const double* xc, int nzc, int nyc, int nxc, double* rf, double* pf, int linear, int mode) {
   if (linear) {
     size_t n = (size_t)nzc * nyc * nxc;
-    k_prolong8<<<blocks_for(n, 256), 256, 0, st>>>(xc, nzc, nyc, nxc, rf, pf, mode); ++g_launches;
+    launch_k(k_prolong8, blocks_for(n, 256), 256, 0, st, xc, nzc, nyc, nxc, rf, pf, mode);
     return;
   }
   size_t n = (size_t)8 * nzc * nyc * nxc;
-  k_prolong<<<blocks_for(n, 256), 256, 0, st>>>(xc, nzc, nyc, nxc, rf, pf, linear, mode); ++g_launches;
+  launch_k(k_prolong, blocks_for(n, 256), 256, 0, st, xc, nzc, nyc, nxc, rf, pf, linear, mode);
 }
 
 // =====================================================================================================
@@ -1211,7 +1427,7 @@ __global__ void k_gather_place(const double* __restrict__ x, int nzl, int nys, i
 }
 void launch_gather_place(cudaStream_t st, const double* x, int nzl, int nys, int nxs, double* y, int ny, int nx, int l, int m) {
   (void)nx; size_t n = (size_t)nzl * nys * nxs;
-  k_gather_place<<<blocks_for(n, 256), 256, 0, st>>>(x, nzl, nys, nxs, y, ny, l, m); ++g_launches;
+  launch_k(k_gather_place, blocks_for(n, 256), 256, 0, st, x, nzl, nys, nxs, y, ny, l, m);
 }
 __global__ void k_split(const double* __restrict__ x, int nzl, int ny, double* __restrict__ y, int nys, int nxs, int l, int m) {
   size_t n = (size_t)nzl * (nys + 2) * (nxs + 2);
@@ -1222,7 +1438,7 @@ __global__ void k_split(const double* __restrict__ x, int nzl, int ny, double* _
 }
 void launch_split(cudaStream_t st, const double* x, int nzl, int ny, int nx, double* y, int nys, int nxs, int l, int m) {
   (void)nx; size_t n = (size_t)nzl * (nys + 2) * (nxs + 2);
-  k_split<<<blocks_for(n, 256), 256, 0, st>>>(x, nzl, ny, y, nys, nxs, l, m); ++g_launches;
+  launch_k(k_split, blocks_for(n, 256), 256, 0, st, x, nzl, ny, y, nys, nxs, l, m);
 }
 
 // =====================================================================================================
@@ -1237,10 +1453,10 @@ __global__ void k_aos8_to_soa(const double* __restrict__ aos, double* const* __r
   for (; e < npts * 8; e += stride) planes[e & 7][e >> 3] = aos[e];
 }
 void launch_soa_to_aos8(cudaStream_t st, double* const* planes_dev, double* aos, size_t npts) {
-  k_soa_to_aos8<<<capped_blocks(npts * 8, 256), 256, 0, st>>>(planes_dev, aos, npts); ++g_launches;
+  launch_k(k_soa_to_aos8, capped_blocks(npts * 8, 256), 256, 0, st, planes_dev, aos, npts);
 }
 void launch_aos8_to_soa(cudaStream_t st, const double* aos, double* const* planes_dev, size_t npts) {
-  k_aos8_to_soa<<<capped_blocks(npts * 8, 256), 256, 0, st>>>(aos, planes_dev, npts); ++g_launches;
+  launch_k(k_aos8_to_soa, capped_blocks(npts * 8, 256), 256, 0, st, aos, planes_dev, npts);
 }
 
 }  // namespace mgb

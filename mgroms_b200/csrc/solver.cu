@@ -72,6 +72,7 @@ struct Level {
   double *pack8[8] = {nullptr}, *unp8[8] = {nullptr};         // nh=2 staging (setup)
   double *partials = nullptr; int npartials = 0;
   Halo1Flags hf{};
+  unsigned* gridbar = nullptr;                                // barrier + exit counters of the cooperative relax kernel
   P2PBox box{};                                               // peer-memory mailbox of this level (multi-GPU, when S.p2p)
   bool bottom_diag = true;
   double rho = 0.0;
@@ -103,6 +104,7 @@ struct Solver {
   double last_ms = 0; int last_iters = 0;
   bool fused_prolong = true;
   bool use_small = true;             // fused single-CTA relaxation on small neighbour-free levels
+  bool use_mid = true;               // fused cooperative relaxation (grid barriers) on mid-size neighbour-free levels
   bool use_graph = true;             // replay one captured F-cycle (+ residual) per outer iteration
   bool fuse_halo = true;             // neighbour-free levels: relax kernels write the Neumann halo themselves
   bool fuse_bc = true;               // neighbour-free levels: kernels B and C fused
@@ -259,6 +261,10 @@ static int relax(int lev, int nsweeps) {
     bool lonely = true; for (int q = 0; q < 8; ++q) lonely &= g.d.neighb[q] < 0;
     if (S.use_small && lonely && relax_small_supported(g.v)) {
       launch_relax_small(S.st, g.v, nsweeps, (real_matrix && g.bottom_diag) ? 1 : 0);
+      return 0;
+    }
+    if (S.use_mid && lonely && relax_mid_supported(g.v)) {
+      launch_relax_mid(S.st, g.v, nsweeps, (real_matrix && g.bottom_diag) ? 1 : 0, g.gridbar);
       return 0;
     }
     const bool rank1 = real_matrix && g.bottom_diag;
@@ -641,6 +647,7 @@ static int init(int nx, int ny, int nz, int npx, int npy, int rank, const char* 
     RC(dalloc(&g.cw, (size_t)(d.nz + 1) * n2));
     RC(dalloc(&g.tab, (size_t)4 * (d.nz + 1)));
     if (lev == 1) { RC(dalloc(&g.dzw, (size_t)(d.nz + 1) * n2)); RC(dalloc(&g.zxdy, n3)); RC(dalloc(&g.zydx, n3)); }
+    { double* q = nullptr; RC(dalloc(&q, 2)); g.gridbar = (unsigned*)q; }
     g.npartials = residual_num_partials(g.v);
     RC(dalloc(&g.partials, (size_t)g.npartials));
     { void* pp = nullptr; CU(cudaMalloc(&pp, 8 * sizeof(double*))); S.allocs.push_back(pp); g.planes_dev = (double**)pp;
@@ -667,6 +674,8 @@ static int init(int nx, int ny, int nz, int npx, int npy, int rank, const char* 
   S.fused_prolong = !(ex && ex[0] == '1');
   const char* ns = std::getenv("MGB_NO_SMALL_KERNEL");
   S.use_small = !(ns && ns[0] == '1');
+  const char* nm = std::getenv("MGB_NO_MID_KERNEL");
+  S.use_mid = !(nm && nm[0] == '1');
   const char* nf = std::getenv("MGB_NO_FUSED_HALO");
   S.fuse_halo = !(nf && nf[0] == '1');
   const char* nb = std::getenv("MGB_NO_FUSED_BC");
