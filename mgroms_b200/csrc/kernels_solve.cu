@@ -1093,10 +1093,11 @@ __global__ void __launch_bounds__(512, 1) k_relax_mid(LevelView L, int nsweeps, 
   if (threadIdx.x == 0) { __threadfence(); if (atomicAdd(bar + 1, 1u) == (unsigned)G - 1) { bar[0] = 0; bar[1] = 0; } }
 }
 static int mid_tc(const LevelView& L) { (void)L; return 64; }
+static size_t mid_limit() { static const size_t v = []() { const char* e = std::getenv("MGB_MID_LIMIT"); return e ? (size_t)std::atoll(e) : (size_t)1500000; }(); return v; }
 bool relax_mid_supported(const LevelView& L) {
   const bool nz_ok = (L.nz == 2 || L.nz == 4 || L.nz == 8 || L.nz == 16 || L.nz == 32);
   const size_t n3 = (size_t)L.nz * (L.ny + 2) * (L.nx + 2);
-  return nz_ok && (L.ny % 2 == 0) && n3 <= (size_t)1500000 && L.rb_W <= RB_WMAX;   // chunked recurrence only
+  return nz_ok && (L.ny % 2 == 0) && n3 <= mid_limit() && L.rb_W <= RB_WMAX;   // chunked recurrence only
 }
 void launch_relax_mid(cudaStream_t st, const LevelView& L, int nsweeps, int rank1, unsigned* bar) {
   const int TC = mid_tc(L);
@@ -1143,7 +1144,8 @@ bool relax_small_supported(const LevelView& L) {
   // single-CTA relaxation pays off on tiny levels only; a 2-level (nz = 2) grid may be a little wider (coarsest level of a multi-GPU job)
   static const bool no_mid = []() { const char* e = std::getenv("MGB_NO_MID_KERNEL"); return e && e[0] == '1'; }();
   if (no_mid) return nz_ok && (L.ny % 2 == 0) && (n2 <= (size_t)34 * 34 || (L.nz == 2 && n2 <= (size_t)66 * 34));
-  return nz_ok && (L.ny % 2 == 0) && n2 <= (size_t)18 * 18;       // larger levels: the cooperative multi-CTA kernel
+  // larger levels go to the cooperative multi-CTA kernel (~7 us per colour floor); a single CTA beats that on 16x16 and on 2-level grids up to 32x32
+  return nz_ok && (L.ny % 2 == 0) && (n2 <= (size_t)18 * 18 || (L.nz == 2 && n2 <= (size_t)34 * 34));
 }
 void launch_relax_small(cudaStream_t st, const LevelView& L, int nsweeps, int rank1) {
   const size_t n2 = (size_t)(L.ny + 2) * (L.nx + 2);
