@@ -140,3 +140,15 @@ def bench_geometry(kind: str, nx, ny, nz, npx, npy, rank=0):
     if kind == "cuc":
         return cuc(nx, ny, nz, npx, npy, rank), CUC_VERT
     raise ValueError(kind)
+
+
+def bmask_rmask(nx, ny, npx=1, npy=1, rank=0):
+    """rmask of the reference drivers when bmask=.true. (src/mg_testseamount.f90:97-101): ones, with the halo row / column
+    zeroed on every side that has no neighbour rank (fill_halo_2D_bmask, src/mg_mpi_exchange.f90:357-391).  Shape (nx+2, ny+2)."""
+    pi, pj = rank % npx, rank // npx
+    m = np.ones((nx + 2, ny + 2))
+    if pj == 0: m[:, 0] = 0.0          # south
+    if pi == npx - 1: m[-1, :] = 0.0   # east
+    if pj == npy - 1: m[:, -1] = 0.0   # north
+    if pi == 0: m[0, :] = 0.0          # west
+    return m

@@ -141,7 +141,7 @@ struct Rank {
   int rank = 0, pi = 0, pj = 0;
   std::vector<Grid> grid;      // grid[lev], lev = 1..nlevs (index 0 unused)
   Store mem;
-  A2 rmask;
+  A2 rmask; bool bmask = false;
   std::vector<double> u, v, w; // model layout (i,j,k), i fastest (nhydro.f90:55-59)
 };
 
@@ -175,7 +175,6 @@ static int define_grids(World& W, int nxl, int nyl, int nzl) {
   W.nlevs = find_grid_levels(W.npx, W.npy, nxl, nyl, nzl);
   if (W.nlevs < 1) { W.err = "grid too small: nlevs < 1"; return 1; }
   if (P.aggressive) { W.err = "aggressive coarsening is unfinished in the reference (mg_intergrids.f90:243)"; return 1; }
-  if (P.bmask) { W.err = "bmask=.true. not restated (SURVEY 8f-3)"; return 1; }
   for (int r = 0; r < W.nranks; ++r) {
     Rank& K = W.R[r];
     K.rank = r; K.pj = r / W.npx; K.pi = r % W.npx;          // mg_grids.f90:593-594
@@ -366,6 +365,7 @@ static A3 sel_dy(Grid& g) { return as3(g.dy); }
 static A3 sel_zeta(Grid& g) { return as3(g.zeta); }
 static A3 sel_h(Grid& g) { return as3(g.h); }
 static A3 sel_d3nz(Grid& g) { return g.dummy3Dnz; }
+static A3 sel_cA(Grid& g) { A3 v; v.d = g.cA.d; v.nzl = 8 * g.nz; v.ny = g.ny; v.nx = g.nx; v.nh = 1; return v; }   // cA(8,nz,j,i) as an (8 nz)-level field
 
 // mg_mpi_exchange.f90:1555-1571 global_sum
 static double global_sum(World& W, int lev, const std::vector<double>& loc) {
@@ -428,10 +428,13 @@ static void setup_zr_zw(const World& W, Grid& g) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// define_matrix  (mg_define_matrix.f90:211-680), bmask = .false.
+// define_matrix  (mg_define_matrix.f90:211-680); umask/vmask = 1 unless bmask (:255-275)
 // ---------------------------------------------------------------------------------------------
-static void define_matrix(Grid& g, int lev) {
+// rm: the level's rmask (0:ny+1,0:nx+1) -- the caller's at level 1, ones with a zeroed physical halo below (:155-161)
+static void define_matrix_coef(Grid& g, int lev, const A2& rm, bool bmask) {
   const int nx = g.nx, ny = g.ny, nz = g.nz;
+  auto UM = [&](int j, int i) -> double { if (!bmask) return 1.0; return (i >= 1 && i <= nx + 1 && j >= 0 && j <= ny + 1) ? rm(j, i - 1) * rm(j, i) : 0.0; };
+  auto VM = [&](int j, int i) -> double { if (!bmask) return 1.0; return (i >= 0 && i <= nx + 1 && j >= 1 && j <= ny + 1) ? rm(j - 1, i) * rm(j, i) : 0.0; };
   const A2 &dx = g.dx, &dy = g.dy; const A3 &zr = g.zr, &zw = g.zw, &cw = g.cw; const A4& cA = g.cA;
   const double hlf = 0.5, qrt = 0.25, one = 1.0;
   auto ZYDX = [&](int k, int j, int i) { return ((hlf * (zr(k, j + 1, i) - zr(k, j - 1, i))) / dy(j, i)) * dx(j, i); };
@@ -461,48 +464,67 @@ static void define_matrix(Grid& g, int lev) {
   // ---- k = 1 (:352-485)
   { const int k = 1;
     for (int i = 1; i <= nx; ++i) for (int j = 1; j <= ny + 1; ++j) {
-      cA(3, k, j, i) = qrt * (ZYDX(k + 1, j, i) + ZYDX(k, j - 1, i));
+      cA(3, k, j, i) = qrt * (ZYDX(k + 1, j, i) + ZYDX(k, j - 1, i)) * VM(j, i);
       cA(4, k, j, i) = ARY(k, j, i) / (hlf * (dy(j, i) + dy(j - 1, i)))
                        - (SQ(ZYDX(k, j, i)) / (cw(k, j, i) + cw(k + 1, j, i)) + SQ(ZYDX(k, j - 1, i)) / (cw(k, j - 1, i) + cw(k + 1, j - 1, i)))
                        - qrt * (ZYDX(k, j - 1, i) - ZYDX(k, j, i));
+      if (bmask)   // :375-389, i-j cross terms at a lateral wall; the second slope is written with /dy*dx in the reference (kept)
+        cA(4, k, j, i) = (cA(4, k, j, i)
+                          - (hlf * ZXDY(k, j - 1, i) * ZYDX(k, j - 1, i) / (cw(k, j - 1, i) + cw(k + 1, j - 1, i)) * (UM(j - 1, i + 1) - UM(j - 1, i))
+                             - hlf * (((hlf * (zr(k, j, i + 1) - zr(k, j, i - 1))) / dy(j, i)) * dx(j, i)) * ZYDX(k, j, i) / (cw(k, j, i) + cw(k + 1, j, i)) * (UM(j, i + 1) - UM(j, i)))) * VM(j, i);
     }
     for (int i = 1; i <= nx + 1; ++i) for (int j = 1; j <= ny; ++j) {
-      cA(6, k, j, i) = qrt * (ZXDY(k + 1, j, i) + ZXDY(k, j, i - 1));
+      cA(6, k, j, i) = qrt * (ZXDY(k + 1, j, i) + ZXDY(k, j, i - 1)) * UM(j, i);
       cA(7, k, j, i) = ARX(k, j, i) / (hlf * (dx(j, i) + dx(j, i - 1)))
                        - (SQ(ZXDY(k, j, i)) / (cw(k, j, i) + cw(k + 1, j, i)) + SQ(ZXDY(k, j, i - 1)) / (cw(k, j, i - 1) + cw(k + 1, j, i - 1)))
                        - qrt * (ZXDY(k, j, i - 1) - ZXDY(k, j, i));
+      if (bmask)   // :417-433
+        cA(7, k, j, i) = (cA(7, k, j, i)
+                          - (hlf * ZXDY(k, j, i - 1) * ZYDX(k, j, i - 1) / (cw(k, j, i - 1) + cw(k + 1, j, i - 1)) * (VM(j + 1, i - 1) - VM(j, i - 1))
+                             - hlf * (((hlf * (zr(k, j, i + 1) - zr(k, j, i - 1))) / dy(j, i)) * dx(j, i)) * ZYDX(k, j, i) / (cw(k, j, i) + cw(k + 1, j, i)) * (VM(j + 1, i) - VM(j, i)))) * UM(j, i);
     }
     for (int i = 1; i <= nx + 1; ++i) for (int j = 0; j <= ny; ++j)       // couples (1,j,i) <-> (1,j+1,i-1)
-      cA(5, k, j, i) = hlf * ZXDY(k, j + 1, i) * ZYDX(k, j + 1, i) / (cw(k, j + 1, i) + cw(k + 1, j + 1, i))
-                     + hlf * ZXDY(k, j, i - 1) * ZYDX(k, j, i - 1) / (cw(k, j, i - 1) + cw(k + 1, j, i - 1));
+      cA(5, k, j, i) = hlf * ZXDY(k, j + 1, i) * ZYDX(k, j + 1, i) / (cw(k, j + 1, i) + cw(k + 1, j + 1, i)) * UM(j + 1, i) * VM(j + 1, i)
+                     + hlf * ZXDY(k, j, i - 1) * ZYDX(k, j, i - 1) / (cw(k, j, i - 1) + cw(k + 1, j, i - 1)) * UM(j, i) * VM(j + 1, i - 1);
     for (int i = 1; i <= nx + 1; ++i) for (int j = 1; j <= ny + 1; ++j)   // couples (1,j,i) <-> (1,j-1,i-1)
-      cA(8, k, j, i) = -(hlf * ZXDY(k, j - 1, i) * ZYDX(k, j - 1, i) / (cw(k, j - 1, i) + cw(k + 1, j - 1, i)))
-                       - hlf * ZXDY(k, j, i - 1) * ZYDX(k, j, i - 1) / (cw(k, j, i - 1) + cw(k + 1, j, i - 1));
+      cA(8, k, j, i) = -(hlf * ZXDY(k, j - 1, i) * ZYDX(k, j - 1, i) / (cw(k, j - 1, i) + cw(k + 1, j - 1, i)) * UM(j - 1, i) * VM(j, i))
+                       - hlf * ZXDY(k, j, i - 1) * ZYDX(k, j, i - 1) / (cw(k, j, i - 1) + cw(k + 1, j, i - 1)) * UM(j, i) * VM(j, i - 1);
   }
   // ---- k = 2 .. nz-1 (:491-560)
-  for (int i = 1; i <= nx; ++i) for (int j = 1; j <= ny; ++j) for (int k = 2; k <= nz - 1; ++k) cA(2, k, j, i) = cw(k, j, i);
+  for (int i = 1; i <= nx; ++i) for (int j = 1; j <= ny; ++j) for (int k = 2; k <= nz - 1; ++k) {
+    cA(2, k, j, i) = cw(k, j, i);
+    if (bmask)     // :497-509, i-k and j-k cross terms at a lateral wall
+      cA(2, k, j, i) = cA(2, k, j, i) - qrt * (ZXDY(k - 1, j, i) - ZXDY(k, j, i)) * (UM(j, i + 1) - UM(j, i))
+                                      - qrt * (ZYDX(k - 1, j, i) - ZYDX(k, j, i)) * (VM(j + 1, i) - VM(j, i));
+  }
   for (int i = 1; i <= nx; ++i) for (int j = 1; j <= ny + 1; ++j) for (int k = 2; k <= nz - 1; ++k) {
-    cA(3, k, j, i) = qrt * (ZYDX(k + 1, j, i) + ZYDX(k, j - 1, i));
-    cA(4, k, j, i) = ARY(k, j, i) / (hlf * (dy(j, i) + dy(j - 1, i)));
-    cA(5, k, j, i) = -qrt * (ZYDX(k - 1, j, i) + ZYDX(k, j - 1, i));
+    cA(3, k, j, i) = qrt * (ZYDX(k + 1, j, i) + ZYDX(k, j - 1, i)) * VM(j, i);
+    cA(4, k, j, i) = ARY(k, j, i) / (hlf * (dy(j, i) + dy(j - 1, i))) * VM(j, i);
+    cA(5, k, j, i) = -qrt * (ZYDX(k - 1, j, i) + ZYDX(k, j - 1, i)) * VM(j, i);
   }
   for (int i = 1; i <= nx + 1; ++i) for (int j = 1; j <= ny; ++j) for (int k = 2; k <= nz - 1; ++k) {
-    cA(6, k, j, i) = qrt * (ZXDY(k + 1, j, i) + ZXDY(k, j, i - 1));
-    cA(7, k, j, i) = ARX(k, j, i) / (hlf * (dx(j, i) + dx(j, i - 1)));
-    cA(8, k, j, i) = -qrt * (ZXDY(k - 1, j, i) + ZXDY(k, j, i - 1));
+    cA(6, k, j, i) = qrt * (ZXDY(k + 1, j, i) + ZXDY(k, j, i - 1)) * UM(j, i);
+    cA(7, k, j, i) = ARX(k, j, i) / (hlf * (dx(j, i) + dx(j, i - 1))) * UM(j, i);
+    cA(8, k, j, i) = -qrt * (ZXDY(k - 1, j, i) + ZXDY(k, j, i - 1)) * UM(j, i);
   }
   // ---- k = nz (:566-609)
   { const int k = nz;
     for (int i = 1; i <= nx; ++i) for (int j = 1; j <= ny; ++j) cA(2, k, j, i) = cw(k, j, i);
     for (int i = 1; i <= nx; ++i) for (int j = 1; j <= ny + 1; ++j) {
-      cA(4, k, j, i) = ARY(k, j, i) / (hlf * (dy(j, i) + dy(j - 1, i))) + qrt * (-ZYDX(k, j - 1, i) + ZYDX(k, j, i));
-      cA(5, k, j, i) = -qrt * (ZYDX(k - 1, j, i) + ZYDX(k, j - 1, i));
+      cA(4, k, j, i) = (ARY(k, j, i) / (hlf * (dy(j, i) + dy(j - 1, i))) + qrt * (-ZYDX(k, j - 1, i) + ZYDX(k, j, i))) * VM(j, i);
+      cA(5, k, j, i) = -qrt * (ZYDX(k - 1, j, i) + ZYDX(k, j - 1, i)) * VM(j, i);
     }
     for (int i = 1; i <= nx + 1; ++i) for (int j = 1; j <= ny; ++j) {
-      cA(7, k, j, i) = ARX(k, j, i) / (hlf * (dx(j, i) + dx(j, i - 1))) + qrt * (-ZXDY(k, j, i - 1) + ZXDY(k, j, i));
-      cA(8, k, j, i) = -qrt * (ZXDY(k - 1, j, i) + ZXDY(k, j, i - 1));
+      cA(7, k, j, i) = (ARX(k, j, i) / (hlf * (dx(j, i) + dx(j, i - 1))) + qrt * (-ZXDY(k, j, i - 1) + ZXDY(k, j, i))) * UM(j, i);
+      cA(8, k, j, i) = -qrt * (ZXDY(k - 1, j, i) + ZXDY(k, j, i - 1)) * UM(j, i);
     }
   }
+}
+// the diagonal (:616-657), after the cA halo exchange that bmask adds (:611-613)
+static void define_matrix_diag(Grid& g) {
+  const int nx = g.nx, ny = g.ny, nz = g.nz;
+  const A2 &dx = g.dx, &dy = g.dy; const A3 &zr = g.zr, &cw = g.cw; const A4& cA = g.cA;
+  const double hlf = 0.5;
   // ---- diagonal (:616-657)
   for (int i = 1; i <= nx; ++i) for (int j = 1; j <= ny; ++j) {
     int k = 1;
@@ -566,12 +588,31 @@ static void define_matrices(World& W) {
     fill_halo(W, lev, sel_dx); fill_halo(W, lev, sel_dy); fill_halo(W, lev, sel_zeta); fill_halo(W, lev, sel_h);
     FOR_RANKS(W) setup_zr_zw(W, W.R[rk].grid[lev]);
     fill_halo(W, lev, sel_zr); fill_halo(W, lev, sel_zw);
-    FOR_RANKS(W) define_matrix(W.R[rk].grid[lev], lev);
+    const bool bmask = W.P.bmask;
+    FOR_RANKS(W) {
+      Rank& K = W.R[rk]; Grid& g = K.grid[lev];
+      std::vector<double> ones;
+      A2 rm = K.rmask;                                       // level 1: the caller's mask (:73-79)
+      if (lev > 1) {                                         // :155-161 ones, physical halo zeroed by fill_halo_2D_bmask (mg_mpi_exchange.f90:357-391)
+        ones.assign((size_t)(g.ny + 2) * (g.nx + 2), 1.0);
+        rm.d = ones.data(); rm.ny = g.ny; rm.nx = g.nx;
+        if (bmask) {
+          if (g.neighb[0] < 0) for (int i = 0; i <= g.nx + 1; ++i) rm(0, i) = 0.0;
+          if (g.neighb[1] < 0) for (int j = 0; j <= g.ny + 1; ++j) rm(j, g.nx + 1) = 0.0;
+          if (g.neighb[2] < 0) for (int i = 0; i <= g.nx + 1; ++i) rm(g.ny + 1, i) = 0.0;
+          if (g.neighb[3] < 0) for (int j = 0; j <= g.ny + 1; ++j) rm(j, 0) = 0.0;
+        }
+      }
+      define_matrix_coef(g, lev, rm, bmask);
+    }
+    if (bmask && W.nranks > 1)                               // fill_halo_4D (mg_mpi_exchange.f90:1245-1530): plain exchange, no physical fill
+      FOR_RANKS(W) { Grid& g = W.R[rk].grid[lev]; halo_phase2(g, sel_cA(g), W, lev, sel_cA); }
+    FOR_RANKS(W) define_matrix_diag(W.R[rk].grid[lev]);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// compute_rhs (mg_compute_rhs.f90:14-379) and correct_uvw (mg_correct_uvw.f90:15-115); bmask=.false.
+// compute_rhs (mg_compute_rhs.f90:14-379) and correct_uvw (mg_correct_uvw.f90:15-115); umask = vmask = 1 unless bmask
 // ---------------------------------------------------------------------------------------------
 struct UVW {
   double *u, *v, *w; int nx, ny, nz;
@@ -583,6 +624,9 @@ struct UVW {
 static void rhs_uf(Rank& K) {
   Grid& g = K.grid[1]; const int nx = g.nx, ny = g.ny, nz = g.nz;
   UVW m{K.u.data(), K.v.data(), K.w.data(), nx, ny, nz};
+  const A2& rm_ = K.rmask; const bool bm_ = K.bmask;      // umask / vmask (mg_compute_rhs.f90:53-72)
+  auto UM = [&](int j, int i) -> double { if (!bm_) return 1.0; return (i >= 1 && i <= nx + 1 && j >= 0 && j <= ny + 1) ? rm_(j, i - 1) * rm_(j, i) : 0.0; };
+  auto VM = [&](int j, int i) -> double { if (!bm_) return 1.0; return (i >= 0 && i <= nx + 1 && j >= 1 && j <= ny + 1) ? rm_(j - 1, i) * rm_(j, i) : 0.0; };
   const A2 &dx = g.dx, &dy = g.dy, &rmask = K.rmask; const A3 &zw = g.zw, &dzw = g.dzw, &zxdy = g.zxdy, &zydx = g.zydx, &cw = g.cw;
   A3 uf = g.dummy3Dnz; const double qrt = 0.25, hlf = 0.5, two = 2.0;
   std::fill(g.b.d, g.b.d + g.b.size(), 0.0);
@@ -593,17 +637,17 @@ static void rhs_uf(Rank& K) {
       - (+zxdy(k, j, i) * zxdy(k, j, i) / (cw(k, j, i) + cw(k + 1, j, i)) + zxdy(k, j, i - 1) * zxdy(k, j, i - 1) / (cw(k, j, i - 1) + cw(k + 1, j, i - 1)))
           * (hlf * (dx(j, i) + dx(j, i - 1))) * m.U(i, j, k)
       - (+zxdy(k, j, i) * zydx(k, j, i) / (cw(k, j, i) + cw(k + 1, j, i))
-            * hlf * (hlf * (dy(j, i) + dy(j - 1, i)) * m.V(i, j, k) * 1.0 + hlf * (dy(j + 1, i) + dy(j, i)) * m.V(i, j + 1, k) * 1.0)
+            * hlf * (hlf * (dy(j, i) + dy(j - 1, i)) * m.V(i, j, k) * VM(j, i) + hlf * (dy(j + 1, i) + dy(j, i)) * m.V(i, j + 1, k) * VM(j + 1, i))
          + zxdy(k, j, i - 1) * zydx(k, j, i - 1) / (cw(k, j, i - 1) + cw(k + 1, j, i - 1))
-            * hlf * (hlf * (dy(j, i - 1) + dy(j - 1, i - 1)) * m.V(i - 1, j, k) * 1.0 + hlf * (dy(j + 1, i - 1) + dy(j, i - 1)) * m.V(i - 1, j + 1, k) * 1.0))) * 1.0;
+            * hlf * (hlf * (dy(j, i - 1) + dy(j - 1, i - 1)) * m.V(i - 1, j, k) * VM(j, i - 1) + hlf * (dy(j + 1, i - 1) + dy(j, i - 1)) * m.V(i - 1, j + 1, k) * VM(j + 1, i - 1)))) * UM(j, i);
     for (k = 2; k <= nz - 1; ++k)
       uf(k, j, i) = (qrt * (zw(k + 1, j, i) - zw(k, j, i) + zw(k + 1, j, i - 1) - zw(k, j, i - 1)) * (dy(j, i) + dy(j, i - 1)) * m.U(i, j, k)
         - qrt * (+zxdy(k, j, i) * dzw(k, j, i) * m.Wv(i, j, k - 1) * rmask(j, i) + zxdy(k, j, i) * dzw(k + 1, j, i) * m.Wv(i, j, k + 1 - 1) * rmask(j, i)
-                 + zxdy(k, j, i - 1) * dzw(k, j, i - 1) * m.Wv(i - 1, j, k - 1) * rmask(j, i - 1) + zxdy(k, j, i - 1) * dzw(k + 1, j, i - 1) * m.Wv(i - 1, j, k + 1 - 1) * rmask(j, i - 1))) * 1.0;
+                 + zxdy(k, j, i - 1) * dzw(k, j, i - 1) * m.Wv(i - 1, j, k - 1) * rmask(j, i - 1) + zxdy(k, j, i - 1) * dzw(k + 1, j, i - 1) * m.Wv(i - 1, j, k + 1 - 1) * rmask(j, i - 1))) * UM(j, i);
     k = nz;
     uf(k, j, i) = (qrt * (zw(k + 1, j, i) - zw(k, j, i) + zw(k + 1, j, i - 1) - zw(k, j, i - 1)) * (dy(j, i) + dy(j, i - 1)) * m.U(i, j, k)
       - qrt * (+zxdy(k, j, i) * dzw(k, j, i) * m.Wv(i, j, k - 1) * rmask(j, i) + zxdy(k, j, i) * two * dzw(k + 1, j, i) * m.Wv(i, j, k + 1 - 1) * rmask(j, i)
-               + zxdy(k, j, i - 1) * dzw(k, j, i - 1) * m.Wv(i - 1, j, k - 1) * rmask(j, i - 1) + zxdy(k, j, i - 1) * two * dzw(k + 1, j, i - 1) * m.Wv(i - 1, j, k + 1 - 1) * rmask(j, i - 1))) * 1.0;
+               + zxdy(k, j, i - 1) * dzw(k, j, i - 1) * m.Wv(i - 1, j, k - 1) * rmask(j, i - 1) + zxdy(k, j, i - 1) * two * dzw(k + 1, j, i - 1) * m.Wv(i - 1, j, k + 1 - 1) * rmask(j, i - 1))) * UM(j, i);
   }
 }
 static void rhs_uf_div(Rank& K) {
@@ -613,6 +657,9 @@ static void rhs_uf_div(Rank& K) {
 static void rhs_vf(Rank& K) {
   Grid& g = K.grid[1]; const int nx = g.nx, ny = g.ny, nz = g.nz;
   UVW m{K.u.data(), K.v.data(), K.w.data(), nx, ny, nz};
+  const A2& rm_ = K.rmask; const bool bm_ = K.bmask;      // umask / vmask (mg_compute_rhs.f90:53-72)
+  auto UM = [&](int j, int i) -> double { if (!bm_) return 1.0; return (i >= 1 && i <= nx + 1 && j >= 0 && j <= ny + 1) ? rm_(j, i - 1) * rm_(j, i) : 0.0; };
+  auto VM = [&](int j, int i) -> double { if (!bm_) return 1.0; return (i >= 0 && i <= nx + 1 && j >= 1 && j <= ny + 1) ? rm_(j - 1, i) * rm_(j, i) : 0.0; };
   const A2 &dx = g.dx, &dy = g.dy, &rmask = K.rmask; const A3 &zw = g.zw, &dzw = g.dzw, &zxdy = g.zxdy, &zydx = g.zydx, &cw = g.cw;
   A3 vf = g.dummy3Dnz; const double qrt = 0.25, hlf = 0.5, two = 2.0;
   for (int i = 1; i <= nx; ++i) for (int j = 1; j <= ny + 1; ++j) {
@@ -622,17 +669,17 @@ static void rhs_vf(Rank& K) {
       - (+zydx(k, j, i) * zydx(k, j, i) / (cw(k, j, i) + cw(k + 1, j, i)) + zydx(k, j - 1, i) * zydx(k, j - 1, i) / (cw(k, j - 1, i) + cw(k + 1, j - 1, i)))
           * hlf * (dy(j, i) + dy(j - 1, i)) * m.V(i, j, k)
       - (+zxdy(k, j, i) * zydx(k, j, i) / (cw(k, j, i) + cw(k + 1, j, i))
-            * hlf * (hlf * (dx(j, i) + dx(j, i - 1)) * m.U(i, j, k) * 1.0 + hlf * (dx(j, i + 1) + dx(j, i)) * m.U(i + 1, j, k) * 1.0)
+            * hlf * (hlf * (dx(j, i) + dx(j, i - 1)) * m.U(i, j, k) * UM(j, i) + hlf * (dx(j, i + 1) + dx(j, i)) * m.U(i + 1, j, k) * UM(j, i + 1))
          + zxdy(k, j - 1, i) * zydx(k, j - 1, i) / (cw(k, j - 1, i) + cw(k + 1, j - 1, i))
-            * hlf * (hlf * (dx(j - 1, i) + dx(j - 1, i - 1)) * m.U(i, j - 1, k) * 1.0 + hlf * (dx(j - 1, i + 1) + dx(j - 1, i)) * m.U(i + 1, j - 1, k) * 1.0))) * 1.0;
+            * hlf * (hlf * (dx(j - 1, i) + dx(j - 1, i - 1)) * m.U(i, j - 1, k) * UM(j - 1, i) + hlf * (dx(j - 1, i + 1) + dx(j - 1, i)) * m.U(i + 1, j - 1, k) * UM(j - 1, i + 1)))) * VM(j, i);
     for (k = 2; k <= nz - 1; ++k)
       vf(k, j, i) = (qrt * (zw(k + 1, j, i) - zw(k, j, i) + zw(k + 1, j - 1, i) - zw(k, j - 1, i)) * (dx(j, i) + dx(j - 1, i)) * m.V(i, j, k)
         - qrt * (+zydx(k, j, i) * dzw(k, j, i) * m.Wv(i, j, k - 1) * rmask(j, i) + zydx(k, j, i) * dzw(k + 1, j, i) * m.Wv(i, j, k + 1 - 1) * rmask(j, i)
-                 + zydx(k, j - 1, i) * dzw(k, j - 1, i) * m.Wv(i, j - 1, k - 1) * rmask(j - 1, i) + zydx(k, j - 1, i) * dzw(k + 1, j - 1, i) * m.Wv(i, j - 1, k + 1 - 1) * rmask(j - 1, i))) * 1.0;
+                 + zydx(k, j - 1, i) * dzw(k, j - 1, i) * m.Wv(i, j - 1, k - 1) * rmask(j - 1, i) + zydx(k, j - 1, i) * dzw(k + 1, j - 1, i) * m.Wv(i, j - 1, k + 1 - 1) * rmask(j - 1, i))) * VM(j, i);
     k = nz;
     vf(k, j, i) = (qrt * (zw(k + 1, j, i) - zw(k, j, i) + zw(k + 1, j - 1, i) - zw(k, j - 1, i)) * (dx(j, i) + dx(j - 1, i)) * m.V(i, j, k)
       - qrt * (+zydx(k, j, i) * dzw(k, j, i) * m.Wv(i, j, k - 1) * rmask(j, i) + zydx(k, j, i) * two * dzw(k + 1, j, i) * m.Wv(i, j, k + 1 - 1) * rmask(j, i)
-               + zydx(k, j - 1, i) * dzw(k, j - 1, i) * m.Wv(i, j - 1, k - 1) * rmask(j - 1, i) + zydx(k, j - 1, i) * two * dzw(k + 1, j - 1, i) * m.Wv(i, j - 1, k + 1 - 1) * rmask(j - 1, i))) * 1.0;
+               + zydx(k, j - 1, i) * dzw(k, j - 1, i) * m.Wv(i, j - 1, k - 1) * rmask(j - 1, i) + zydx(k, j - 1, i) * two * dzw(k + 1, j - 1, i) * m.Wv(i, j - 1, k + 1 - 1) * rmask(j - 1, i))) * VM(j, i);
   }
 }
 static void rhs_vf_div(Rank& K) {
@@ -642,31 +689,34 @@ static void rhs_vf_div(Rank& K) {
 static void rhs_wf(Rank& K) {
   Grid& g = K.grid[1]; const int nx = g.nx, ny = g.ny, nz = g.nz;
   UVW m{K.u.data(), K.v.data(), K.w.data(), nx, ny, nz};
+  const A2& rm_ = K.rmask; const bool bm_ = K.bmask;      // umask / vmask (mg_compute_rhs.f90:53-72)
+  auto UM = [&](int j, int i) -> double { if (!bm_) return 1.0; return (i >= 1 && i <= nx + 1 && j >= 0 && j <= ny + 1) ? rm_(j, i - 1) * rm_(j, i) : 0.0; };
+  auto VM = [&](int j, int i) -> double { if (!bm_) return 1.0; return (i >= 0 && i <= nx + 1 && j >= 1 && j <= ny + 1) ? rm_(j - 1, i) * rm_(j, i) : 0.0; };
   const A2 &dx = g.dx, &dy = g.dy; const A3 &dzw = g.dzw, &zxdy = g.zxdy, &zydx = g.zydx, &cw = g.cw;
   A3 wf = g.dummy3Dnzp; const double qrt = 0.25, hlf = 0.5;
   for (int i = 1; i <= nx; ++i) for (int j = 1; j <= ny; ++j) {
     wf(1, j, i) = 0.0;
     for (int k = 2; k <= nz; ++k) {
       wf(k, j, i) = cw(k, j, i) * dzw(k, j, i) * m.Wv(i, j, k - 1)
-        - qrt * hlf * (+zxdy(k, j, i) * (dx(j, i) + dx(j, i - 1)) * m.U(i, j, k) * 1.0 + zxdy(k, j, i) * (dx(j, i + 1) + dx(j, i)) * m.U(i + 1, j, k) * 1.0
-                       + zxdy(k - 1, j, i) * (dx(j, i) + dx(j, i - 1)) * m.U(i, j, k - 1) * 1.0 + zxdy(k - 1, j, i) * (dx(j, i + 1) + dx(j, i)) * m.U(i + 1, j, k - 1) * 1.0);
+        - qrt * hlf * (+zxdy(k, j, i) * (dx(j, i) + dx(j, i - 1)) * m.U(i, j, k) * UM(j, i) + zxdy(k, j, i) * (dx(j, i + 1) + dx(j, i)) * m.U(i + 1, j, k) * UM(j, i + 1)
+                       + zxdy(k - 1, j, i) * (dx(j, i) + dx(j, i - 1)) * m.U(i, j, k - 1) * UM(j, i) + zxdy(k - 1, j, i) * (dx(j, i + 1) + dx(j, i)) * m.U(i + 1, j, k - 1) * UM(j, i + 1));
       wf(k, j, i) = wf(k, j, i)
-        - qrt * hlf * (+zydx(k, j, i) * (dy(j, i) + dy(j - 1, i)) * m.V(i, j, k) * 1.0 + zydx(k, j, i) * (dy(j + 1, i) + dy(j, i)) * m.V(i, j + 1, k) * 1.0
-                       + zydx(k - 1, j, i) * (dy(j, i) + dy(j - 1, i)) * m.V(i, j, k - 1) * 1.0 + zydx(k - 1, j, i) * (dy(j + 1, i) + dy(j, i)) * m.V(i, j + 1, k - 1) * 1.0);
+        - qrt * hlf * (+zydx(k, j, i) * (dy(j, i) + dy(j - 1, i)) * m.V(i, j, k) * VM(j, i) + zydx(k, j, i) * (dy(j + 1, i) + dy(j, i)) * m.V(i, j + 1, k) * VM(j + 1, i)
+                       + zydx(k - 1, j, i) * (dy(j, i) + dy(j - 1, i)) * m.V(i, j, k - 1) * VM(j, i) + zydx(k - 1, j, i) * (dy(j + 1, i) + dy(j, i)) * m.V(i, j + 1, k - 1) * VM(j + 1, i));
     }
     int k = nz + 1;
     wf(k, j, i) = cw(k, j, i) * dzw(k, j, i) * m.Wv(i, j, k - 1)
-      - hlf * hlf * (+zxdy(k - 1, j, i) * (dx(j, i) + dx(j, i - 1)) * m.U(i, j, k - 1) * 1.0 + zxdy(k - 1, j, i) * (dx(j, i + 1) + dx(j, i)) * m.U(i + 1, j, k - 1) * 1.0)
-      - hlf * hlf * (+zydx(k - 1, j, i) * (dy(j, i) + dy(j - 1, i)) * m.V(i, j, k - 1) * 1.0 + zydx(k - 1, j, i) * (dy(j + 1, i) + dy(j, i)) * m.V(i, j + 1, k - 1) * 1.0);
+      - hlf * hlf * (+zxdy(k - 1, j, i) * (dx(j, i) + dx(j, i - 1)) * m.U(i, j, k - 1) * UM(j, i) + zxdy(k - 1, j, i) * (dx(j, i + 1) + dx(j, i)) * m.U(i + 1, j, k - 1) * UM(j, i + 1))
+      - hlf * hlf * (+zydx(k - 1, j, i) * (dy(j, i) + dy(j - 1, i)) * m.V(i, j, k - 1) * VM(j, i) + zydx(k - 1, j, i) * (dy(j + 1, i) + dy(j, i)) * m.V(i, j + 1, k - 1) * VM(j + 1, i));
     for (k = 1; k <= nz; ++k) g.b(k, j, i) = g.b(k, j, i) + wf(k + 1, j, i) - wf(k, j, i);
   }
 }
 static void compute_rhs(World& W) {
-  FOR_RANKS(W) rhs_uf(W.R[rk]);
-  fill_halo(W, 1, sel_d3nz, 'u');
+  FOR_RANKS(W) { W.R[rk].bmask = W.P.bmask; rhs_uf(W.R[rk]); }
+  if (!W.P.bmask) fill_halo(W, 1, sel_d3nz, 'u');          // mg_compute_rhs.f90:170-172: with bmask the masks close the walls
   FOR_RANKS(W) rhs_uf_div(W.R[rk]);
   FOR_RANKS(W) rhs_vf(W.R[rk]);
-  fill_halo(W, 1, sel_d3nz, 'v');
+  if (!W.P.bmask) fill_halo(W, 1, sel_d3nz, 'v');
   FOR_RANKS(W) rhs_vf_div(W.R[rk]);
   FOR_RANKS(W) rhs_wf(W.R[rk]);
 }
@@ -675,13 +725,16 @@ static void correct_uvw(World& W) {
     Rank& K = W.R[rk]; Grid& g = K.grid[1]; const int nx = g.nx, ny = g.ny, nz = g.nz;
     UVW m{K.u.data(), K.v.data(), K.w.data(), nx, ny, nz};
     const A3& p = g.p; const double hlf = 0.5, one = 1.0;
+    const A2& rm_ = K.rmask; const bool bm_ = W.P.bmask;    // mg_correct_uvw.f90:48-68
+    auto UM = [&](int j, int i) -> double { if (!bm_) return 1.0; return (i >= 1 && i <= nx + 1 && j >= 0 && j <= ny + 1) ? rm_(j, i - 1) * rm_(j, i) : 0.0; };
+    auto VM = [&](int j, int i) -> double { if (!bm_) return 1.0; return (i >= 0 && i <= nx + 1 && j >= 1 && j <= ny + 1) ? rm_(j - 1, i) * rm_(j, i) : 0.0; };
     for (int i = 1; i <= nx + 1; ++i) for (int j = 0; j <= ny + 1; ++j) for (int k = 1; k <= nz; ++k) {
       double dxu = hlf * (g.dx(j, i) + g.dx(j, i - 1));
-      m.U(i, j, k) = m.U(i, j, k) - one / dxu * (p(k, j, i) - p(k, j, i - 1)) * 1.0;
+      m.U(i, j, k) = m.U(i, j, k) - one / dxu * (p(k, j, i) - p(k, j, i - 1)) * UM(j, i);
     }
     for (int i = 0; i <= nx + 1; ++i) for (int j = 1; j <= ny + 1; ++j) for (int k = 1; k <= nz; ++k) {
       double dyv = hlf * (g.dy(j, i) + g.dy(j - 1, i));
-      m.V(i, j, k) = m.V(i, j, k) - one / dyv * (p(k, j, i) - p(k, j - 1, i)) * 1.0;
+      m.V(i, j, k) = m.V(i, j, k) - one / dyv * (p(k, j, i) - p(k, j - 1, i)) * VM(j, i);
     }
     for (int i = 0; i <= nx + 1; ++i) for (int j = 0; j <= ny + 1; ++j) {
       for (int k = 2; k <= nz; ++k) {

@@ -186,7 +186,7 @@ def make_case(kind, nx, ny, nz, npx=1, npy=1, uvw="wminus1", bench_dx=False, **p
             dx, dy, zeta, h = tc.cuc(nx, ny, nz, npx, npy, r); vert = tc.CUC_VERT
         else:
             raise ValueError(kind)
-        o.set_geometry(r, dx, dy, zeta, h)
+        o.set_geometry(r, dx, dy, zeta, h, tc.bmask_rmask(nx, ny, npx, npy, r) if params.get("bmask") else None)
         if uvw == "wminus1":
             o.set_uvw(r, *tc.uvw_wminus1(nx, ny, nz))
         else:

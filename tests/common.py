@@ -24,7 +24,7 @@ def velocities(mode, nx, ny, nz, npx=1, npy=1, rank=0):
 def make_oracle(kind, nx, ny, nz, uvw="wminus1", bench_dx=False, **params):
     o = Oracle(nx, ny, nz, 1, 1, **params)
     (dx, dy, zeta, h), vert = geometry(kind, nx, ny, nz, bench_dx=bench_dx)
-    o.set_geometry(0, dx, dy, zeta, h)
+    o.set_geometry(0, dx, dy, zeta, h, tc.bmask_rmask(nx, ny) if params.get("bmask") else None)
     o.set_uvw(0, *velocities(uvw, nx, ny, nz))
     o.matrices(vert["hc"], vert["theta_b"], vert["theta_s"])
     return o
@@ -36,7 +36,7 @@ def make_product(nh, kind, nx, ny, nz, bench_dx=False, **params):
     nh.set_params(**params)
     nh.nhydro_init(nx, ny, nz, 1, 1)
     (dx, dy, zeta, h), vert = geometry(kind, nx, ny, nz, bench_dx=bench_dx)
-    nh.nhydro_matrices(dx, dy, zeta, h, None, vert["hc"], vert["theta_b"], vert["theta_s"])
+    nh.nhydro_matrices(dx, dy, zeta, h, tc.bmask_rmask(nx, ny) if params.get("bmask") else None, vert["hc"], vert["theta_b"], vert["theta_s"])
     return nh
 
 

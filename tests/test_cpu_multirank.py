@@ -73,14 +73,16 @@ def test_gather_split_roundtrip_and_family_layout():
         assert np.array_equal(o.get("dummy3", lev, r), big[l * nxs:l * nxs + nxs + 2, m * nys:m * nys + nys + 2])
 
 
+@pytest.mark.parametrize("bmask", [False, True])
 @pytest.mark.parametrize("npx,npy", [(2, 2), (4, 2)])
-def test_operators_are_decomposition_invariant(npx, npy):
+def test_operators_are_decomposition_invariant(npx, npy, bmask):
     """Everything except the red-black bottom recurrence (which restarts at sub-domain edges, as in the reference) must
     not depend on the decomposition: matrices, rhs, residual, restriction, prolongation."""
     nxg, nyg, nz = 32, 32, 8
-    o1 = make_case("rndtopo", nxg, nyg, nz, 1, 1, uvw="random", nsmall=4)
-    on = make_case("rndtopo", nxg // npx, nyg // npy, nz, npx, npy, uvw="random", nsmall=4)      # nsmall=4: no gathering at level 2
+    o1 = make_case("rndtopo", nxg, nyg, nz, 1, 1, uvw="random", nsmall=4, bmask=bmask)
+    on = make_case("rndtopo", nxg // npx, nyg // npy, nz, npx, npy, uvw="random", nsmall=4, bmask=bmask)      # nsmall=4: no gathering at level 2
     assert np.array_equal(assemble(on, "cA", 1, npx, npy), o1.get("cA")[1:-1, 1:-1])
+    assert np.array_equal(assemble(on, "cA", 2, npx, npy), o1.get("cA", 2)[1:-1, 1:-1])
     o1.compute_rhs(); on.compute_rhs()
     assert np.array_equal(assemble(on, "b", 1, npx, npy), o1.get("b")[1:-1, 1:-1])
     r1, rn = o1.residual(1), on.residual(1)
