@@ -138,7 +138,6 @@ int plan_levels(const Params& P, int nx, int ny, int nz, int npx, int npy, int r
   auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
   if (!pow2(npx) || !pow2(npy) || !pow2(nx) || !pow2(ny)) { msg = "horizontal dimensions and process counts must be powers of 2 (reference 'assumptions')"; return 1; }
   if (P.aggressive) { msg = "aggressive coarsening is not available (the reference stops: src/mg_intergrids.f90:243)"; return 1; }
-  if (P.bmask) { msg = "bmask=.true. is not built yet (SURVEY section 8f-3)"; return 1; }
 
   const int nxg = npx * nx, nyg = npy * ny;
   const int nl1 = ilog2_floor_ratio(std::min(nxg, nyg), 4);   // ncoarsest = 4

@@ -95,11 +95,16 @@ void launch_zrzw(cudaStream_t st, const double* h, const double* zeta, const dou
 struct MatrixView {
   int nx, ny, nz, lev1;
   const double *dx, *dy, *zr, *zw;
+  const double *rmask; int bmask;     // level mask (0:ny+1,0:nx+1) and namelist bmask: umask/vmask = 1 unless bmask
   double *cw, *dzw, *zxdy, *zydx;
   double* cA[8];
   double *bet, *g, *c5b, *c8b, *g1;
 };
-void launch_define_matrix(cudaStream_t st, const MatrixView& M);
+void launch_define_matrix(cudaStream_t st, const MatrixView& M);        // coefficients + diagonal + derived (no cA exchange in between)
+void launch_define_matrix_coef(cudaStream_t st, const MatrixView& M);   // cw, metrics, cA(2..8)
+void launch_define_matrix_diag(cudaStream_t st, const MatrixView& M);   // cA(1), bet, g, g1  (after the cA halo exchange that bmask adds)
+// rmask of a coarse level: ones, halo zeroed on sides without neighbour when bmask (src/mg_define_matrix.f90:155-161)
+void launch_level_rmask(cudaStream_t st, double* rm, int ny, int nx, Halo1Flags f, int bmask);
 void launch_refresh_derived(cudaStream_t st, const MatrixView& M);   // c5b, c8b, bet, g, g1 from the cA planes
 void launch_rho(cudaStream_t st, const MatrixView& M, double* out_dev);   // contraction factor of the bottom recurrence
 // max(|c5b|,|c8b|) > 0 ?  result (0/1) written to *flag_dev
@@ -115,7 +120,8 @@ struct RhsView {
   const double *ut, *vt, *wt;   // k-fastest: ut(nz, ny+2, nx+1) i=1..nx+1 ; vt(nz, ny+1, nx+2) j=1..ny+1 ; wt(nz+1, ny+2, nx+2)
   double *flux;                 // scratch (nz+1, ny+2, nx+2)
   double *b;
-  int west_phys, east_phys, south_phys, north_phys;
+  int west_phys, east_phys, south_phys, north_phys;   // wall faces to zero (lbc_null); all 0 with bmask (the masks close the walls)
+  int bmask;
 };
 void launch_rhs_uf(cudaStream_t st, const RhsView& R);       // flux(k,j,i) = uf, i=1..nx+1, j=1..ny (+ wall zero)
 void launch_rhs_vf(cudaStream_t st, const RhsView& R);
@@ -125,6 +131,7 @@ struct CorrView {
   int nx, ny, nz;
   const double *dx, *dy, *zr, *zw, *p;
   double *ut, *vt, *wt;
+  const double* rmask; int bmask;
 };
 void launch_correct_uvw(cudaStream_t st, const CorrView& C);
 

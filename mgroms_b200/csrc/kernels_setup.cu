@@ -52,11 +52,14 @@ void launch_zrzw(cudaStream_t st, const double* h, const double* zeta, const dou
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// define_matrix (src/mg_define_matrix.f90:211-680), bmask = .false.
+// define_matrix (src/mg_define_matrix.f90:211-680); umask = vmask = 1 unless bmask (:255-275)
 // Accessors take FORTRAN indices (K = 1..nz, j, i incl. halos)
 // ---------------------------------------------------------------------------------------------------------
 struct MAcc {
-  int nz, ny, nx; const double *dx, *dy, *zr, *zw, *cw;
+  int nz, ny, nx; const double *dx, *dy, *zr, *zw, *cw; const double* rm; int bmask;
+  __device__ __forceinline__ double RMK(int j, int i) const { return rm[(size_t)j + (size_t)(ny + 2) * i]; }
+  __device__ __forceinline__ double UM(int j, int i) const { if (!bmask) return 1.0; return (i >= 1 && i <= nx + 1 && j >= 0 && j <= ny + 1) ? RMK(j, i - 1) * RMK(j, i) : 0.0; }
+  __device__ __forceinline__ double VM(int j, int i) const { if (!bmask) return 1.0; return (i >= 0 && i <= nx + 1 && j >= 1 && j <= ny + 1) ? RMK(j - 1, i) * RMK(j, i) : 0.0; }
   __device__ __forceinline__ double DX(int j, int i) const { return dx[(size_t)j + (size_t)(ny + 2) * i]; }
   __device__ __forceinline__ double DY(int j, int i) const { return dy[(size_t)j + (size_t)(ny + 2) * i]; }
   __device__ __forceinline__ double ZR(int K, int j, int i) const { return zr[(size_t)(K - 1) + (size_t)nz * ((size_t)(j + 1) + (size_t)(ny + 4) * (size_t)(i + 1))]; }
@@ -77,7 +80,7 @@ __global__ void k_cw_metrics(MatrixView M) {
   size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
   const int K = 1 + (int)(e % nzp); size_t t = e / nzp; const int j = (int)(t % (ny + 2)), i = (int)(t / (ny + 2));
-  MAcc A{nz, ny, nx, M.dx, M.dy, M.zr, M.zw, M.cw};
+  MAcc A{nz, ny, nx, M.dx, M.dy, M.zr, M.zw, M.cw, M.rmask, M.bmask};
   const double Arz = A.DX(j, i) * A.DY(j, i);
   const double dz = (K == 1) ? (A.ZR(1, j, i) - A.ZW(1, j, i)) : (K <= nz ? (A.ZR(K, j, i) - A.ZR(K - 1, j, i)) : (A.ZW(K, j, i) - A.ZR(K - 1, j, i)));
   M.cw[e] = (Arz / dz) * (1.0 + sq(0.5 * (A.ZW(K, j, i + 1) - A.ZW(K, j, i - 1)) / A.DX(j, i)) + sq(0.5 * (A.ZW(K, j + 1, i) - A.ZW(K, j - 1, i)) / A.DY(j, i)));
@@ -98,41 +101,59 @@ __global__ void k_coef(MatrixView M) {
   size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
   const int K = 1 + (int)(e % nz); size_t t = e / nz; const int j = (int)(t % (ny + 2)), i = (int)(t / (ny + 2));
-  MAcc A{nz, ny, nx, M.dx, M.dy, M.zr, M.zw, M.cw};
+  MAcc A{nz, ny, nx, M.dx, M.dy, M.zr, M.zw, M.cw, M.rmask, M.bmask};
   const double qrt = 0.25, hlf = 0.5;
   const bool jt = (i >= 1 && i <= nx && j >= 1 && j <= ny + 1);
   const bool it = (i >= 1 && i <= nx + 1 && j >= 1 && j <= ny);
-  if (K >= 2 && i >= 1 && i <= nx && j >= 1 && j <= ny) M.cA[1][e] = A.CW(K, j, i);
+  if (K >= 2 && i >= 1 && i <= nx && j >= 1 && j <= ny) {
+    double v = A.CW(K, j, i);
+    if (M.bmask && K <= nz - 1)     // :497-509, i-k and j-k cross terms at a lateral wall (not at k = nz in the reference)
+      v = v - qrt * (A.ZXDY(K - 1, j, i) - A.ZXDY(K, j, i)) * (A.UM(j, i + 1) - A.UM(j, i))
+            - qrt * (A.ZYDX(K - 1, j, i) - A.ZYDX(K, j, i)) * (A.VM(j + 1, i) - A.VM(j, i));
+    M.cA[1][e] = v;
+  }
   if (jt) {
-    if (K <= nz - 1) M.cA[2][e] = qrt * (A.ZYDX(K + 1, j, i) + A.ZYDX(K, j - 1, i));
+    const double vm = A.VM(j, i);
+    if (K <= nz - 1) M.cA[2][e] = qrt * (A.ZYDX(K + 1, j, i) + A.ZYDX(K, j - 1, i)) * vm;
     const double base = A.ARY(K, j, i) / (hlf * (A.DY(j, i) + A.DY(j - 1, i)));
-    if (K == 1)
-      M.cA[3][e] = base - (sq(A.ZYDX(K, j, i)) / A.CWS(j, i) + sq(A.ZYDX(K, j - 1, i)) / A.CWS(j - 1, i)) - qrt * (A.ZYDX(K, j - 1, i) - A.ZYDX(K, j, i));
-    else if (K == nz)
-      M.cA[3][e] = base + qrt * (-A.ZYDX(K, j - 1, i) + A.ZYDX(K, j, i));
+    if (K == 1) {
+      double v = base - (sq(A.ZYDX(K, j, i)) / A.CWS(j, i) + sq(A.ZYDX(K, j - 1, i)) / A.CWS(j - 1, i)) - qrt * (A.ZYDX(K, j - 1, i) - A.ZYDX(K, j, i));
+      if (M.bmask)    // :375-389 ; the second slope is written /dy*dx in the reference (kept)
+        v = (v - (hlf * A.ZXDY(K, j - 1, i) * A.ZYDX(K, j - 1, i) / A.CWS(j - 1, i) * (A.UM(j - 1, i + 1) - A.UM(j - 1, i))
+                  - hlf * (((hlf * (A.ZR(K, j, i + 1) - A.ZR(K, j, i - 1))) / A.DY(j, i)) * A.DX(j, i)) * A.ZYDX(K, j, i) / A.CWS(j, i) * (A.UM(j, i + 1) - A.UM(j, i)))) * vm;
+      M.cA[3][e] = v;
+    } else if (K == nz)
+      M.cA[3][e] = (base + qrt * (-A.ZYDX(K, j - 1, i) + A.ZYDX(K, j, i))) * vm;
     else
-      M.cA[3][e] = base;
-    if (K >= 2) M.cA[4][e] = -qrt * (A.ZYDX(K - 1, j, i) + A.ZYDX(K, j - 1, i));
+      M.cA[3][e] = base * vm;
+    if (K >= 2) M.cA[4][e] = -qrt * (A.ZYDX(K - 1, j, i) + A.ZYDX(K, j - 1, i)) * vm;
   }
   if (it) {
-    if (K <= nz - 1) M.cA[5][e] = qrt * (A.ZXDY(K + 1, j, i) + A.ZXDY(K, j, i - 1));
+    const double um = A.UM(j, i);
+    if (K <= nz - 1) M.cA[5][e] = qrt * (A.ZXDY(K + 1, j, i) + A.ZXDY(K, j, i - 1)) * um;
     const double base = A.ARX(K, j, i) / (hlf * (A.DX(j, i) + A.DX(j, i - 1)));
-    if (K == 1)
-      M.cA[6][e] = base - (sq(A.ZXDY(K, j, i)) / A.CWS(j, i) + sq(A.ZXDY(K, j, i - 1)) / A.CWS(j, i - 1)) - qrt * (A.ZXDY(K, j, i - 1) - A.ZXDY(K, j, i));
-    else if (K == nz)
-      M.cA[6][e] = base + qrt * (-A.ZXDY(K, j, i - 1) + A.ZXDY(K, j, i));
+    if (K == 1) {
+      double v = base - (sq(A.ZXDY(K, j, i)) / A.CWS(j, i) + sq(A.ZXDY(K, j, i - 1)) / A.CWS(j, i - 1)) - qrt * (A.ZXDY(K, j, i - 1) - A.ZXDY(K, j, i));
+      if (M.bmask)    // :417-433
+        v = (v - (hlf * A.ZXDY(K, j, i - 1) * A.ZYDX(K, j, i - 1) / A.CWS(j, i - 1) * (A.VM(j + 1, i - 1) - A.VM(j, i - 1))
+                  - hlf * (((hlf * (A.ZR(K, j, i + 1) - A.ZR(K, j, i - 1))) / A.DY(j, i)) * A.DX(j, i)) * A.ZYDX(K, j, i) / A.CWS(j, i) * (A.VM(j + 1, i) - A.VM(j, i)))) * um;
+      M.cA[6][e] = v;
+    } else if (K == nz)
+      M.cA[6][e] = (base + qrt * (-A.ZXDY(K, j, i - 1) + A.ZXDY(K, j, i))) * um;
     else
-      M.cA[6][e] = base;
-    if (K >= 2) M.cA[7][e] = -qrt * (A.ZXDY(K - 1, j, i) + A.ZXDY(K, j, i - 1));
+      M.cA[6][e] = base * um;
+    if (K >= 2) M.cA[7][e] = -qrt * (A.ZXDY(K - 1, j, i) + A.ZXDY(K, j, i - 1)) * um;
   }
   if (K == 1) {
     const size_t c2d = (size_t)j + (size_t)(ny + 2) * i;
     if (i >= 1 && i <= nx + 1 && j >= 0 && j <= ny) {         // couples (1,j,i) <-> (1,j+1,i-1)
-      const double v = hlf * A.ZXDY(1, j + 1, i) * A.ZYDX(1, j + 1, i) / A.CWS(j + 1, i) + hlf * A.ZXDY(1, j, i - 1) * A.ZYDX(1, j, i - 1) / A.CWS(j, i - 1);
+      const double v = hlf * A.ZXDY(1, j + 1, i) * A.ZYDX(1, j + 1, i) / A.CWS(j + 1, i) * A.UM(j + 1, i) * A.VM(j + 1, i)
+                     + hlf * A.ZXDY(1, j, i - 1) * A.ZYDX(1, j, i - 1) / A.CWS(j, i - 1) * A.UM(j, i) * A.VM(j + 1, i - 1);
       M.cA[4][e] = v; M.c5b[c2d] = v;
     }
     if (i >= 1 && i <= nx + 1 && j >= 1 && j <= ny + 1) {     // couples (1,j,i) <-> (1,j-1,i-1)
-      const double v = -(hlf * A.ZXDY(1, j - 1, i) * A.ZYDX(1, j - 1, i) / A.CWS(j - 1, i)) - hlf * A.ZXDY(1, j, i - 1) * A.ZYDX(1, j, i - 1) / A.CWS(j, i - 1);
+      const double v = -(hlf * A.ZXDY(1, j - 1, i) * A.ZYDX(1, j - 1, i) / A.CWS(j - 1, i) * A.UM(j - 1, i) * A.VM(j, i))
+                       - hlf * A.ZXDY(1, j, i - 1) * A.ZYDX(1, j, i - 1) / A.CWS(j, i - 1) * A.UM(j, i) * A.VM(j, i - 1);
       M.cA[7][e] = v; M.c8b[c2d] = v;
     }
   }
@@ -158,7 +179,7 @@ __global__ void k_diag(MatrixView M) {
         - c6[idx] - c6[idx + si - 1] - c8[idx] - c8[idx + si + 1]
         - c3[idx] - c3[idx + sj - 1] - c5[idx] - c5[idx + sj + 1];
   } else {
-    MAcc A{nz, ny, nx, M.dx, M.dy, M.zr, M.zw, M.cw};
+    MAcc A{nz, ny, nx, M.dx, M.dy, M.zr, M.zw, M.cw, M.rmask, M.bmask};
     const int K = nz; const double hlf = 0.5;
     v = -c2[idx] - A.CW(K + 1, j, i)
         + hlf * (hlf * (A.ZR(K, j, i + 2) - A.ZR(K, j, i)) / A.DX(j, i + 1)) * A.DY(j, i + 1)
@@ -196,12 +217,27 @@ __global__ void k_thomas_setup(MatrixView M) {
   M.g1[(size_t)j + (size_t)ny2 * i] = x;
 }
 
-void launch_define_matrix(cudaStream_t st, const MatrixView& M) {
+void launch_define_matrix_coef(cudaStream_t st, const MatrixView& M) {
   const size_t np1 = (size_t)(M.nz + 1) * (M.ny + 2) * (M.nx + 2), n = (size_t)M.nz * (M.ny + 2) * (M.nx + 2);
   k_cw_metrics<<<blocks_for(np1, 256), 256, 0, st>>>(M); ++g_launches;
   k_coef<<<blocks_for(n, 256), 256, 0, st>>>(M); ++g_launches;
+}
+void launch_define_matrix_diag(cudaStream_t st, const MatrixView& M) {
   k_diag<<<blocks_for((size_t)M.nz * M.ny * M.nx, 256), 256, 0, st>>>(M); ++g_launches;
   k_thomas_setup<<<blocks_for((size_t)M.ny * M.nx, 128), 128, 0, st>>>(M); ++g_launches;
+}
+void launch_define_matrix(cudaStream_t st, const MatrixView& M) { launch_define_matrix_coef(st, M); launch_define_matrix_diag(st, M); }
+__global__ void k_level_rmask(double* __restrict__ rm, int ny, int nx, Halo1Flags f, int bmask) {
+  const int ny2 = ny + 2;
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ny2 * (nx + 2)) return;
+  const int j = e % ny2, i = e / ny2;
+  double v = 1.0;
+  if (bmask && ((j == 0 && !f.south) || (i == nx + 1 && !f.east) || (j == ny + 1 && !f.north) || (i == 0 && !f.west))) v = 0.0;
+  rm[e] = v;
+}
+void launch_level_rmask(cudaStream_t st, double* rm, int ny, int nx, Halo1Flags f, int bmask) {
+  k_level_rmask<<<blocks_for((size_t)(ny + 2) * (nx + 2), 256), 256, 0, st>>>(rm, ny, nx, f, bmask); ++g_launches;
 }
 
 __global__ void k_copy_bottom(MatrixView M) {
@@ -288,10 +324,12 @@ void launch_transpose_kji_to_ijk(cudaStream_t st, const double* src, double* dst
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// compute_rhs (src/mg_compute_rhs.f90:14-379), bmask = .false. (umask = vmask = 1)
+// compute_rhs (src/mg_compute_rhs.f90:14-379); umask = vmask = 1 unless bmask (:53-72)
 // ---------------------------------------------------------------------------------------------------------
 struct RAcc {
-  int nz, ny, nx; const double *dx, *dy, *zw, *dzw, *zxdy, *zydx, *cw, *rmask, *ut, *vt, *wt;
+  int nz, ny, nx; const double *dx, *dy, *zw, *dzw, *zxdy, *zydx, *cw, *rmask, *ut, *vt, *wt; int bmask;
+  __device__ __forceinline__ double UM(int j, int i) const { if (!bmask) return 1.0; return (i >= 1 && i <= nx + 1 && j >= 0 && j <= ny + 1) ? RM(j, i - 1) * RM(j, i) : 0.0; }
+  __device__ __forceinline__ double VM(int j, int i) const { if (!bmask) return 1.0; return (i >= 0 && i <= nx + 1 && j >= 1 && j <= ny + 1) ? RM(j - 1, i) * RM(j, i) : 0.0; }
   __device__ __forceinline__ double DX(int j, int i) const { return dx[(size_t)j + (size_t)(ny + 2) * i]; }
   __device__ __forceinline__ double DY(int j, int i) const { return dy[(size_t)j + (size_t)(ny + 2) * i]; }
   __device__ __forceinline__ double RM(int j, int i) const { return rmask[(size_t)j + (size_t)(ny + 2) * i]; }
@@ -304,7 +342,7 @@ struct RAcc {
   __device__ __forceinline__ double V(int i, int j, int K) const { return vt[(size_t)(K - 1) + (size_t)nz * ((size_t)(j - 1) + (size_t)(ny + 1) * (size_t)i)]; }
   __device__ __forceinline__ double W(int i, int j, int Kw) const { return wt[(size_t)Kw + (size_t)(nz + 1) * ((size_t)j + (size_t)(ny + 2) * (size_t)i)]; }
 };
-__device__ __forceinline__ RAcc racc(const RhsView& R) { return RAcc{R.nz, R.ny, R.nx, R.dx, R.dy, R.zw, R.dzw, R.zxdy, R.zydx, R.cw, R.rmask, R.ut, R.vt, R.wt}; }
+__device__ __forceinline__ RAcc racc(const RhsView& R) { return RAcc{R.nz, R.ny, R.nx, R.dx, R.dy, R.zw, R.dzw, R.zxdy, R.zydx, R.cw, R.rmask, R.ut, R.vt, R.wt, R.bmask}; }
 
 // uf(k,j,i), i = 1..nx+1, j = 1..ny  -> flux(k,j,i) with stride nz ; wall faces zeroed (lbc_null='u')
 __global__ void k_rhs_uf(RhsView R) {
@@ -323,17 +361,17 @@ __global__ void k_rhs_uf(RhsView R) {
          - (+A.ZX(k, j, i) * A.ZX(k, j, i) / (A.CW(k, j, i) + A.CW(k + 1, j, i)) + A.ZX(k, j, i - 1) * A.ZX(k, j, i - 1) / (A.CW(k, j, i - 1) + A.CW(k + 1, j, i - 1)))
                * (hlf * (A.DX(j, i) + A.DX(j, i - 1))) * A.U(i, j, k)
          - (+A.ZX(k, j, i) * A.ZY(k, j, i) / (A.CW(k, j, i) + A.CW(k + 1, j, i))
-                  * hlf * (hlf * (A.DY(j, i) + A.DY(j - 1, i)) * A.V(i, j, k) * 1.0 + hlf * (A.DY(j + 1, i) + A.DY(j, i)) * A.V(i, j + 1, k) * 1.0)
+                  * hlf * (hlf * (A.DY(j, i) + A.DY(j - 1, i)) * A.V(i, j, k) * A.VM(j, i) + hlf * (A.DY(j + 1, i) + A.DY(j, i)) * A.V(i, j + 1, k) * A.VM(j + 1, i))
             + A.ZX(k, j, i - 1) * A.ZY(k, j, i - 1) / (A.CW(k, j, i - 1) + A.CW(k + 1, j, i - 1))
-                  * hlf * (hlf * (A.DY(j, i - 1) + A.DY(j - 1, i - 1)) * A.V(i - 1, j, k) * 1.0 + hlf * (A.DY(j + 1, i - 1) + A.DY(j, i - 1)) * A.V(i - 1, j + 1, k) * 1.0))) * 1.0;
+                  * hlf * (hlf * (A.DY(j, i - 1) + A.DY(j - 1, i - 1)) * A.V(i - 1, j, k) * A.VM(j, i - 1) + hlf * (A.DY(j + 1, i - 1) + A.DY(j, i - 1)) * A.V(i - 1, j + 1, k) * A.VM(j + 1, i - 1)))) * A.UM(j, i);
   } else if (k < nz) {
     v = (arx_u
          - qrt * (+A.ZX(k, j, i) * A.DZW(k, j, i) * A.W(i, j, k - 1) * A.RM(j, i) + A.ZX(k, j, i) * A.DZW(k + 1, j, i) * A.W(i, j, k + 1 - 1) * A.RM(j, i)
-                  + A.ZX(k, j, i - 1) * A.DZW(k, j, i - 1) * A.W(i - 1, j, k - 1) * A.RM(j, i - 1) + A.ZX(k, j, i - 1) * A.DZW(k + 1, j, i - 1) * A.W(i - 1, j, k + 1 - 1) * A.RM(j, i - 1))) * 1.0;
+                  + A.ZX(k, j, i - 1) * A.DZW(k, j, i - 1) * A.W(i - 1, j, k - 1) * A.RM(j, i - 1) + A.ZX(k, j, i - 1) * A.DZW(k + 1, j, i - 1) * A.W(i - 1, j, k + 1 - 1) * A.RM(j, i - 1))) * A.UM(j, i);
   } else {
     v = (arx_u
          - qrt * (+A.ZX(k, j, i) * A.DZW(k, j, i) * A.W(i, j, k - 1) * A.RM(j, i) + A.ZX(k, j, i) * two * A.DZW(k + 1, j, i) * A.W(i, j, k + 1 - 1) * A.RM(j, i)
-                  + A.ZX(k, j, i - 1) * A.DZW(k, j, i - 1) * A.W(i - 1, j, k - 1) * A.RM(j, i - 1) + A.ZX(k, j, i - 1) * two * A.DZW(k + 1, j, i - 1) * A.W(i - 1, j, k + 1 - 1) * A.RM(j, i - 1))) * 1.0;
+                  + A.ZX(k, j, i - 1) * A.DZW(k, j, i - 1) * A.W(i - 1, j, k - 1) * A.RM(j, i - 1) + A.ZX(k, j, i - 1) * two * A.DZW(k + 1, j, i - 1) * A.W(i - 1, j, k + 1 - 1) * A.RM(j, i - 1))) * A.UM(j, i);
   }
   if ((i == 1 && R.west_phys) || (i == nx + 1 && R.east_phys)) v = 0.0;
   R.flux[(size_t)(k - 1) + (size_t)nz * ((size_t)j + (size_t)(ny + 2) * i)] = v;
@@ -355,17 +393,17 @@ __global__ void k_rhs_vf(RhsView R) {
          - (+A.ZY(k, j, i) * A.ZY(k, j, i) / (A.CW(k, j, i) + A.CW(k + 1, j, i)) + A.ZY(k, j - 1, i) * A.ZY(k, j - 1, i) / (A.CW(k, j - 1, i) + A.CW(k + 1, j - 1, i)))
                * hlf * (A.DY(j, i) + A.DY(j - 1, i)) * A.V(i, j, k)
          - (+A.ZX(k, j, i) * A.ZY(k, j, i) / (A.CW(k, j, i) + A.CW(k + 1, j, i))
-                  * hlf * (hlf * (A.DX(j, i) + A.DX(j, i - 1)) * A.U(i, j, k) * 1.0 + hlf * (A.DX(j, i + 1) + A.DX(j, i)) * A.U(i + 1, j, k) * 1.0)
+                  * hlf * (hlf * (A.DX(j, i) + A.DX(j, i - 1)) * A.U(i, j, k) * A.UM(j, i) + hlf * (A.DX(j, i + 1) + A.DX(j, i)) * A.U(i + 1, j, k) * A.UM(j, i + 1))
             + A.ZX(k, j - 1, i) * A.ZY(k, j - 1, i) / (A.CW(k, j - 1, i) + A.CW(k + 1, j - 1, i))
-                  * hlf * (hlf * (A.DX(j - 1, i) + A.DX(j - 1, i - 1)) * A.U(i, j - 1, k) * 1.0 + hlf * (A.DX(j - 1, i + 1) + A.DX(j - 1, i)) * A.U(i + 1, j - 1, k) * 1.0))) * 1.0;
+                  * hlf * (hlf * (A.DX(j - 1, i) + A.DX(j - 1, i - 1)) * A.U(i, j - 1, k) * A.UM(j - 1, i) + hlf * (A.DX(j - 1, i + 1) + A.DX(j - 1, i)) * A.U(i + 1, j - 1, k) * A.UM(j - 1, i + 1)))) * A.VM(j, i);
   } else if (k < nz) {
     v = (ary_v
          - qrt * (+A.ZY(k, j, i) * A.DZW(k, j, i) * A.W(i, j, k - 1) * A.RM(j, i) + A.ZY(k, j, i) * A.DZW(k + 1, j, i) * A.W(i, j, k + 1 - 1) * A.RM(j, i)
-                  + A.ZY(k, j - 1, i) * A.DZW(k, j - 1, i) * A.W(i, j - 1, k - 1) * A.RM(j - 1, i) + A.ZY(k, j - 1, i) * A.DZW(k + 1, j - 1, i) * A.W(i, j - 1, k + 1 - 1) * A.RM(j - 1, i))) * 1.0;
+                  + A.ZY(k, j - 1, i) * A.DZW(k, j - 1, i) * A.W(i, j - 1, k - 1) * A.RM(j - 1, i) + A.ZY(k, j - 1, i) * A.DZW(k + 1, j - 1, i) * A.W(i, j - 1, k + 1 - 1) * A.RM(j - 1, i))) * A.VM(j, i);
   } else {
     v = (ary_v
          - qrt * (+A.ZY(k, j, i) * A.DZW(k, j, i) * A.W(i, j, k - 1) * A.RM(j, i) + A.ZY(k, j, i) * two * A.DZW(k + 1, j, i) * A.W(i, j, k + 1 - 1) * A.RM(j, i)
-                  + A.ZY(k, j - 1, i) * A.DZW(k, j - 1, i) * A.W(i, j - 1, k - 1) * A.RM(j - 1, i) + A.ZY(k, j - 1, i) * two * A.DZW(k + 1, j - 1, i) * A.W(i, j - 1, k + 1 - 1) * A.RM(j - 1, i))) * 1.0;
+                  + A.ZY(k, j - 1, i) * A.DZW(k, j - 1, i) * A.W(i, j - 1, k - 1) * A.RM(j - 1, i) + A.ZY(k, j - 1, i) * two * A.DZW(k + 1, j - 1, i) * A.W(i, j - 1, k + 1 - 1) * A.RM(j - 1, i))) * A.VM(j, i);
   }
   if ((j == 1 && R.south_phys) || (j == ny + 1 && R.north_phys)) v = 0.0;
   R.flux[(size_t)(k - 1) + (size_t)nz * ((size_t)j + (size_t)(ny + 2) * i)] = v;
@@ -384,15 +422,15 @@ __global__ void k_rhs_wf(RhsView R) {
     v = 0.0;
   } else if (k <= nz) {
     v = A.CW(k, j, i) * A.DZW(k, j, i) * A.W(i, j, k - 1)
-        - qrt * hlf * (+A.ZX(k, j, i) * (A.DX(j, i) + A.DX(j, i - 1)) * A.U(i, j, k) * 1.0 + A.ZX(k, j, i) * (A.DX(j, i + 1) + A.DX(j, i)) * A.U(i + 1, j, k) * 1.0
-                       + A.ZX(k - 1, j, i) * (A.DX(j, i) + A.DX(j, i - 1)) * A.U(i, j, k - 1) * 1.0 + A.ZX(k - 1, j, i) * (A.DX(j, i + 1) + A.DX(j, i)) * A.U(i + 1, j, k - 1) * 1.0);
+        - qrt * hlf * (+A.ZX(k, j, i) * (A.DX(j, i) + A.DX(j, i - 1)) * A.U(i, j, k) * A.UM(j, i) + A.ZX(k, j, i) * (A.DX(j, i + 1) + A.DX(j, i)) * A.U(i + 1, j, k) * A.UM(j, i + 1)
+                       + A.ZX(k - 1, j, i) * (A.DX(j, i) + A.DX(j, i - 1)) * A.U(i, j, k - 1) * A.UM(j, i) + A.ZX(k - 1, j, i) * (A.DX(j, i + 1) + A.DX(j, i)) * A.U(i + 1, j, k - 1) * A.UM(j, i + 1));
     v = v
-        - qrt * hlf * (+A.ZY(k, j, i) * (A.DY(j, i) + A.DY(j - 1, i)) * A.V(i, j, k) * 1.0 + A.ZY(k, j, i) * (A.DY(j + 1, i) + A.DY(j, i)) * A.V(i, j + 1, k) * 1.0
-                       + A.ZY(k - 1, j, i) * (A.DY(j, i) + A.DY(j - 1, i)) * A.V(i, j, k - 1) * 1.0 + A.ZY(k - 1, j, i) * (A.DY(j + 1, i) + A.DY(j, i)) * A.V(i, j + 1, k - 1) * 1.0);
+        - qrt * hlf * (+A.ZY(k, j, i) * (A.DY(j, i) + A.DY(j - 1, i)) * A.V(i, j, k) * A.VM(j, i) + A.ZY(k, j, i) * (A.DY(j + 1, i) + A.DY(j, i)) * A.V(i, j + 1, k) * A.VM(j + 1, i)
+                       + A.ZY(k - 1, j, i) * (A.DY(j, i) + A.DY(j - 1, i)) * A.V(i, j, k - 1) * A.VM(j, i) + A.ZY(k - 1, j, i) * (A.DY(j + 1, i) + A.DY(j, i)) * A.V(i, j + 1, k - 1) * A.VM(j + 1, i));
   } else {
     v = A.CW(k, j, i) * A.DZW(k, j, i) * A.W(i, j, k - 1)
-        - hlf * hlf * (+A.ZX(k - 1, j, i) * (A.DX(j, i) + A.DX(j, i - 1)) * A.U(i, j, k - 1) * 1.0 + A.ZX(k - 1, j, i) * (A.DX(j, i + 1) + A.DX(j, i)) * A.U(i + 1, j, k - 1) * 1.0)
-        - hlf * hlf * (+A.ZY(k - 1, j, i) * (A.DY(j, i) + A.DY(j - 1, i)) * A.V(i, j, k - 1) * 1.0 + A.ZY(k - 1, j, i) * (A.DY(j + 1, i) + A.DY(j, i)) * A.V(i, j + 1, k - 1) * 1.0);
+        - hlf * hlf * (+A.ZX(k - 1, j, i) * (A.DX(j, i) + A.DX(j, i - 1)) * A.U(i, j, k - 1) * A.UM(j, i) + A.ZX(k - 1, j, i) * (A.DX(j, i + 1) + A.DX(j, i)) * A.U(i + 1, j, k - 1) * A.UM(j, i + 1))
+        - hlf * hlf * (+A.ZY(k - 1, j, i) * (A.DY(j, i) + A.DY(j - 1, i)) * A.V(i, j, k - 1) * A.VM(j, i) + A.ZY(k - 1, j, i) * (A.DY(j + 1, i) + A.DY(j, i)) * A.V(i, j + 1, k - 1) * A.VM(j + 1, i));
   }
   R.flux[(size_t)(k - 1) + (size_t)nzp * ((size_t)j + (size_t)(ny + 2) * i)] = v;
 }
@@ -427,17 +465,20 @@ __global__ void k_correct_uvw(CorrView C) {
   auto DX = [&](int jj, int ii) { return C.dx[(size_t)jj + (size_t)ny2 * ii]; };
   auto DY = [&](int jj, int ii) { return C.dy[(size_t)jj + (size_t)ny2 * ii]; };
   auto ZR = [&](int K, int jj, int ii) { return C.zr[(size_t)(K - 1) + (size_t)nz * ((size_t)(jj + 1) + (size_t)(ny + 4) * (size_t)(ii + 1))]; };
+  auto RM = [&](int jj, int ii) { return C.rmask[(size_t)jj + (size_t)ny2 * ii]; };
+  auto UM = [&](int jj, int ii) -> double { if (!C.bmask) return 1.0; return (ii >= 1 && ii <= nx + 1 && jj >= 0 && jj <= ny + 1) ? RM(jj, ii - 1) * RM(jj, ii) : 0.0; };   // src/mg_correct_uvw.f90:48-68
+  auto VM = [&](int jj, int ii) -> double { if (!C.bmask) return 1.0; return (ii >= 0 && ii <= nx + 1 && jj >= 1 && jj <= ny + 1) ? RM(jj - 1, ii) * RM(jj, ii) : 0.0; };
   if (kk >= 1) {
     const int K = kk;    // K = 1..nz
     if (i >= 1) {        // u(i,j,K), i = 1..nx+1, j = 0..ny+1
       const double dxu = hlf * (DX(j, i) + DX(j, i - 1));
       double* u = C.ut + ((size_t)(K - 1) + (size_t)nz * ((size_t)j + (size_t)ny2 * (size_t)(i - 1)));
-      *u = *u - one / dxu * (P(K, j, i) - P(K, j, i - 1)) * 1.0;
+      *u = *u - one / dxu * (P(K, j, i) - P(K, j, i - 1)) * UM(j, i);
     }
     if (j >= 1) {        // v(i,j,K), i = 0..nx+1, j = 1..ny+1
       const double dyv = hlf * (DY(j, i) + DY(j - 1, i));
       double* v = C.vt + ((size_t)(K - 1) + (size_t)nz * ((size_t)(j - 1) + (size_t)(ny + 1) * (size_t)i));
-      *v = *v - one / dyv * (P(K, j, i) - P(K, j - 1, i)) * 1.0;
+      *v = *v - one / dyv * (P(K, j, i) - P(K, j - 1, i)) * VM(j, i);
     }
   }
   // w(i,j,kw), kw = 1..nz ; (kw = 0, the bottom, is not corrected)

@@ -72,6 +72,7 @@ struct Level {
   double *pack8[8] = {nullptr}, *unp8[8] = {nullptr};         // nh=2 staging (setup)
   double *partials = nullptr; int npartials = 0;
   Halo1Flags hf{};
+  double* rmaskl = nullptr;                                   // coarse-level rmask (ones; physical halo zeroed when bmask)
   unsigned* gridbar = nullptr;                                // barrier + exit counters of the cooperative relax kernel
   P2PBox box{};                                               // peer-memory mailbox of this level (multi-GPU, when S.p2p)
   bool bottom_diag = true;
@@ -471,6 +472,7 @@ static MatrixView matrix_view(Level& g, int lev) {
   M.dx = g.dx; M.dy = g.dy; M.zr = g.zr; M.zw = g.zw; M.cw = g.cw; M.dzw = g.dzw; M.zxdy = g.zxdy; M.zydx = g.zydx;
   for (int q = 0; q < 8; ++q) M.cA[q] = g.v.cA[q];
   M.bet = g.v.bet; M.g = g.v.g; M.c5b = g.v.c5b; M.c8b = g.v.c8b; M.g1 = g.v.g1;
+  M.rmask = (lev == 1) ? S.rmask : g.rmaskl; M.bmask = S.P.bmask ? 1 : 0;    // level 1: the caller's mask (src/mg_define_matrix.f90:73-79)
   return M;
 }
 
@@ -499,7 +501,15 @@ static int define_matrices() {
     RC(fill_halo(lev, g.zr, g.d.nz, 2)); RC(fill_halo(lev, g.zw, g.d.nz + 1, 2));
     for (int q = 0; q < 8; ++q) launch_fill(S.st, g.v.cA[q], 0.0, g.n3());
     launch_fill(S.st, g.v.c5b, 0.0, g.n2()); launch_fill(S.st, g.v.c8b, 0.0, g.n2());
-    launch_define_matrix(S.st, matrix_view(g, lev));
+    if (lev > 1) launch_level_rmask(S.st, g.rmaskl, g.d.ny, g.d.nx, g.hf, S.P.bmask ? 1 : 0);
+    launch_define_matrix_coef(S.st, matrix_view(g, lev));
+    bool anynb = false; for (int q = 0; q < 8; ++q) anynb |= g.d.neighb[q] >= 0;
+    if (S.P.bmask && anynb) {                                  // fill_halo(lev,cA), src/mg_define_matrix.f90:611-613: plain exchange, no physical fill
+      if (!S.comm) return fail("multi-rank level but mgb_comm_init has not been called");
+      for (int q = 0; q < 8; ++q) RC(exchange(g, g.v.cA[q], g.d.nz, 1));
+    }
+    launch_define_matrix_diag(S.st, matrix_view(g, lev));
+    if (S.P.bmask && anynb) launch_refresh_derived(S.st, matrix_view(g, lev));   // c5b / c8b planes from the exchanged cA
     launch_any_nonzero2(S.st, g.v.c5b, g.v.c8b, g.n2(), S.flag_dev);
     int flag = 1;
     CU(cudaMemcpyAsync(&flag, S.flag_dev, sizeof(int), cudaMemcpyDeviceToHost, S.st));
@@ -576,10 +586,13 @@ static int compute_rhs_device() {
   R.nx = g.d.nx; R.ny = g.d.ny; R.nz = g.d.nz;
   R.dx = g.dx; R.dy = g.dy; R.zw = g.zw; R.dzw = g.dzw; R.zxdy = g.zxdy; R.zydx = g.zydx; R.cw = g.cw; R.rmask = S.rmask;
   R.ut = S.ut; R.vt = S.vt; R.wt = S.wt; R.flux = S.flux; R.b = g.v.b;
-  R.west_phys = !g.hf.west; R.east_phys = !g.hf.east; R.south_phys = !g.hf.south; R.north_phys = !g.hf.north;
+  // bmask: no fill_halo(uf/vf, lbc_null) at all (src/mg_compute_rhs.f90:170-172,271-273); umask / vmask close the walls
+  const bool bm = S.P.bmask;
+  R.bmask = bm ? 1 : 0;
+  R.west_phys = !bm && !g.hf.west; R.east_phys = !bm && !g.hf.east; R.south_phys = !bm && !g.hf.south; R.north_phys = !bm && !g.hf.north;
   launch_fill(S.st, g.v.b, 0.0, g.n3());                      // rhs(:,:,:) = zero  (src/mg_compute_rhs.f90:91)
-  launch_rhs_uf(S.st, R); if (S.nranks > 1) RC(exchange_flux_face('u')); launch_rhs_div(S.st, R, 0);
-  launch_rhs_vf(S.st, R); if (S.nranks > 1) RC(exchange_flux_face('v')); launch_rhs_div(S.st, R, 1);
+  launch_rhs_uf(S.st, R); if (S.nranks > 1 && !bm) RC(exchange_flux_face('u')); launch_rhs_div(S.st, R, 0);
+  launch_rhs_vf(S.st, R); if (S.nranks > 1 && !bm) RC(exchange_flux_face('v')); launch_rhs_div(S.st, R, 1);
   launch_rhs_wf(S.st, R); launch_rhs_div(S.st, R, 2);
   return 0;
 }
@@ -591,7 +604,7 @@ static int set_rmask(const double* rmask) {
 }
 static int correct_uvw_device() {
   Level& g = S.L[0];
-  CorrView C{g.d.nx, g.d.ny, g.d.nz, g.dx, g.dy, g.zr, g.zw, g.v.p, S.ut, S.vt, S.wt};
+  CorrView C{g.d.nx, g.d.ny, g.d.nz, g.dx, g.dy, g.zr, g.zw, g.v.p, S.ut, S.vt, S.wt, S.rmask, S.P.bmask ? 1 : 0};
   launch_correct_uvw(S.st, C);
   return 0;
 }
@@ -642,7 +655,7 @@ static int init(int nx, int ny, int nz, int npx, int npy, int rank, const char* 
     for (int c = 0; c < 8; ++c) RC(dalloc(&g.v.cA[c], n3));
     RC(dalloc(&g.v.bet, n3)); RC(dalloc(&g.v.g, n3));
     RC(dalloc(&g.v.c5b, n2)); RC(dalloc(&g.v.c8b, n2)); RC(dalloc(&g.v.g1, n2)); RC(dalloc(&g.v.q1, n2)); RC(dalloc(&g.v.x1, n2)); RC(dalloc(&g.v.x1b, n2)); RC(dalloc(&g.v.s, n2));
-    RC(dalloc(&g.dx, n2)); RC(dalloc(&g.dy, n2)); RC(dalloc(&g.zeta, n2)); RC(dalloc(&g.h, n2));
+    RC(dalloc(&g.dx, n2)); RC(dalloc(&g.dy, n2)); RC(dalloc(&g.zeta, n2)); RC(dalloc(&g.h, n2)); RC(dalloc(&g.rmaskl, n2));
     RC(dalloc(&g.zr, (size_t)d.nz * (d.ny + 4) * (d.nx + 4))); RC(dalloc(&g.zw, (size_t)(d.nz + 1) * (d.ny + 4) * (d.nx + 4)));
     RC(dalloc(&g.cw, (size_t)(d.nz + 1) * n2));
     RC(dalloc(&g.tab, (size_t)4 * (d.nz + 1)));
@@ -920,7 +933,15 @@ int mgb_fcycle(void) { RC(check_level(1)); RC(fcycle()); return finish(); }
 int mgb_vcycle(int lev1) { RC(check_level(lev1)); RC(vcycle(lev1)); return finish(); }
 int mgb_fill_halo(int lev, const char* name) {
   RC(check_level(lev)); FieldRef f; RC(field_ref(lev, name, f));
-  if (f.is_cA) return fail("cA halo is only exchanged with bmask (not built)");
+  if (f.is_cA) {                                               // fill_halo_4D, src/mg_mpi_exchange.f90:1245-1530
+    Level& g = S.L[lev - 1];
+    bool anynb = false; for (int q = 0; q < 8; ++q) anynb |= g.d.neighb[q] >= 0;
+    if (anynb) { if (!S.comm) return fail("mgb_comm_init has not been called"); for (int q = 0; q < 8; ++q) RC(exchange(g, g.v.cA[q], g.d.nz, 1)); }
+    if (!S.P.bmask) {                                          // Neumann branch of the reference: zero halo where there is no neighbour
+      return fail("fill_halo(cA) without bmask zeroes the physical halo of cA in the reference; it is never called there and is not offered");
+    }
+    return finish();
+  }
   const LevelDims& d = S.L[lev - 1].d; const std::string n = name;
   if (n == "zr") RC(fill_halo(lev, f.ptr, d.nz, 2)); else if (n == "zw") RC(fill_halo(lev, f.ptr, d.nz + 1, 2));
   else if (n == "dx" || n == "dy" || n == "zeta" || n == "h") RC(fill_halo(lev, f.ptr, 1, 1));

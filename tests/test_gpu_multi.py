@@ -35,9 +35,11 @@ def _worker(rank, world, port, cfg, out):
         dist.broadcast_object_list(box, src=0)
         nh.comm_init(box[0])
         (dx, dy, zeta, h), vert = geometry(kind, nx, ny, nz, npx, npy, rank)
-        nh.nhydro_matrices(dx, dy, zeta, h, None, vert["hc"], vert["theta_b"], vert["theta_s"])
+        from mgroms_b200 import testcases as tc
+        rm = tc.bmask_rmask(nx, ny, npx, npy, rank) if params.get("bmask") else None
+        nh.nhydro_matrices(dx, dy, zeta, h, rm, vert["hc"], vert["theta_b"], vert["theta_s"])
         u, v, w = velocities(uvw, nx, ny, nz, npx, npy, rank)
-        nh.compute_rhs(None, u, v, w)
+        nh.compute_rhs(rm, u, v, w)
         res = {"b": nh.get_field("b"), "cA": [nh.get_field("cA", l) for l in range(1, nh.nlevs() + 1)]}
         nh.solve_p()
         res["hist"] = nh.history()[0]; res["p"] = nh.get_field("p")
@@ -72,6 +74,8 @@ CFGS = [
     ("seamount", 16, 16, 16, 2, 2, dict(solver_prec=1e-10, solver_maxiter=20), "random"),
     ("cuc", 16, 32, 8, 2, 2, dict(solver_prec=1e-9, solver_maxiter=20, nsmall=16), "wminus1"),
     ("seamount", 16, 32, 16, 4, 2, dict(solver_prec=1e-10, solver_maxiter=20, nsmall=16), "random"),   # C4-like: two gather stages on 8 GPUs
+    ("rndtopo", 16, 32, 16, 2, 1, dict(solver_prec=1e-10, solver_maxiter=30, bmask=True), "random"),     # bmask: masked walls + cA halo exchange
+    ("seamount", 16, 16, 16, 2, 2, dict(solver_prec=1e-10, solver_maxiter=30, bmask=True, nsmall=16), "random"),
 ]
 
 
