@@ -263,7 +263,7 @@ def main():
                 "algorithmic_bytes_per_launch": BYTES_PER_POINT["relax_colour"] * npts,
                 "achieved_counting_rank1_pass": ach80, "frac_counting_rank1_pass": ach80 / peak,
                 "note": "68 B/pt is SURVEY 8(d)'s figure for the colour; the exact reference sweep order needs a second pass p+=s*g (+12 B/pt), "
-                        "80 B/pt in total -- both fractions are given; k_relax_A4 alone runs at 4.5 TB/s (profiles/)",
+                        "80 B/pt in total -- both fractions are given; k_relax_A4 alone runs at 5.05 TB/s (profiles/)",
                 "others_GBps": {k: BYTES_PER_POINT[k] * npts / (prof[k + "_ms"] * 1e-3) / 1e9 for k in ("residual", "restrict", "prolong")}}
 
     if rank == 0:
