@@ -817,32 +817,41 @@ void launch_relax_C(cudaStream_t st, const LevelView& L, const ColourSet& cs) {
 // replaces 10*nsweeps launches by one.  Only valid when the level has no lateral neighbour rank (single GPU, or
 // a level gathered onto one rank).  Same arithmetic, operation by operation, as kernels A/B/C + halo.
 //   shared memory: six 2-D planes (x1, q1, c5b, c8b, g1, s) of (ny+2)*(nx+2) doubles + per-warp x1 rows
-template <int NZ>
-__global__ void __launch_bounds__(1024) k_relax_small(LevelView L, int nsweeps, int rank1, int all_smem) {
+// ASM (compile time, so that the staged operands are addressed with LDS/STS instead of generic loads):
+//   0: 3-D operands in global memory (L2) ; 1: p, cA2..8, bet staged in shared memory (b and g stay in L2) ; 2: b and g as well
+template <int NZ, int ASM>
+__global__ void __launch_bounds__(1024) k_relax_small(LevelView L, int nsweeps, int rank1) {
+  constexpr int all_smem = ASM;
   extern __shared__ __align__(16) double sm[];
   const int nx = L.nx, ny = L.ny, ny2 = ny + 2, nyc = ny / 2;
   const int n2 = ny2 * (nx + 2);
   double *x1 = sm, *q1 = sm + n2, *c5b = sm + 2 * n2, *c8b = sm + 3 * n2, *g1 = sm + 4 * n2, *ss = sm + 5 * n2, *rows = sm + 6 * n2;   // rows: [8 warps][2][ny2]
   const int sj = NZ; const int si = NZ * ny2;
   // the 3-D operands stay in global memory (L2) or, when the whole level fits (all_smem), are staged in shared memory
-  double* p = L.p;
-  const double* b = L.b;
-  const double *c2 = L.cA[1], *c3 = L.cA[2], *c4 = L.cA[3], *c5 = L.cA[4], *c6 = L.cA[5], *c7 = L.cA[6], *c8 = L.cA[7], *bet = L.bet, *g = L.g;
   const int n3 = NZ * n2;
-  if (all_smem) {        // 1: p, cA2..8, bet staged (b and g stay in L2) ; 2: b and g as well
-    double* base = rows + 16 * ny2;
+  double* const base = rows + 16 * ny2;
+  if constexpr (ASM > 0) {
     const double* src[11] = {L.p, L.cA[1], L.cA[2], L.cA[3], L.cA[4], L.cA[5], L.cA[6], L.cA[7], L.bet, L.b, L.g};
-    const int na = all_smem == 2 ? 11 : 9;
+    constexpr int na = ASM == 2 ? 11 : 9;
     for (int a = 0; a < na; ++a) for (int e = threadIdx.x; e < n3; e += blockDim.x) base[a * n3 + e] = src[a][e];
-    p = base; c2 = base + n3; c3 = base + 2 * n3; c4 = base + 3 * n3; c5 = base + 4 * n3; c6 = base + 5 * n3; c7 = base + 6 * n3;
-    c8 = base + 7 * n3; bet = base + 8 * n3;
-    if (all_smem == 2) { b = base + 9 * n3; g = base + 10 * n3; }
   }
+  double* const p = ASM > 0 ? base : L.p;
+  const double* const c2 = ASM > 0 ? base + n3 : L.cA[1];     const double* const c3 = ASM > 0 ? base + 2 * n3 : L.cA[2];
+  const double* const c4 = ASM > 0 ? base + 3 * n3 : L.cA[3]; const double* const c5 = ASM > 0 ? base + 4 * n3 : L.cA[4];
+  const double* const c6 = ASM > 0 ? base + 5 * n3 : L.cA[5]; const double* const c7 = ASM > 0 ? base + 6 * n3 : L.cA[6];
+  const double* const c8 = ASM > 0 ? base + 7 * n3 : L.cA[7]; const double* const bet = ASM > 0 ? base + 8 * n3 : L.bet;
+  const double* const b = ASM == 2 ? base + 9 * n3 : L.b;     const double* const g = ASM == 2 ? base + 10 * n3 : L.g;
   if (rank1) for (int e = threadIdx.x; e < n2; e += blockDim.x) { c5b[e] = L.c5b[e]; c8b[e] = L.c8b[e]; g1[e] = L.g1[e]; }
   __syncthreads();
   // x1 = p(1,:,:) once; afterwards the final stores of each colour keep it (and the Neumann halo of p) current
   if (rank1) { for (int e = threadIdx.x; e < n2; e += blockDim.x) x1[e] = p[(size_t)e * NZ]; __syncthreads(); }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+#ifdef MGB_SMALL_TIMING
+  long long tA = 0, tB = 0, tC = 0, t0 = clock64();
+#define SM_T(acc) { const long long t1 = clock64(); acc += t1 - t0; t0 = t1; }
+#else
+#define SM_T(acc)
+#endif
   for (int it = 0; it < nsweeps; ++it) for (int rb = 1; rb <= 2; ++rb) {
     // ---- A: thread per column
     for (int c = threadIdx.x; c < nx * nyc; c += blockDim.x) {
@@ -889,6 +898,7 @@ __global__ void __launch_bounds__(1024) k_relax_small(LevelView L, int nsweeps, 
       }
     }
     __syncthreads();
+    SM_T(tA)
     if (rank1) {
       // ---- B: chunked bottom recurrence, one warp per chunk (same chunks and warm-up as kernel B).  When the colour's
       //      columns of a row fit one warp (ny <= 64) the previous row lives in registers and travels by shuffles.
@@ -932,6 +942,7 @@ __global__ void __launch_bounds__(1024) k_relax_small(LevelView L, int nsweeps, 
         }
       }
       __syncthreads();
+      SM_T(tB)
       // ---- C: p += s g on the colour's columns; final values -> Neumann mirrors and the x1 plane
       for (int c = threadIdx.x; c < nx * nyc; c += blockDim.x) {
         const int i = 1 + c / nyc, jc = c % nyc;
@@ -946,8 +957,13 @@ __global__ void __launch_bounds__(1024) k_relax_small(LevelView L, int nsweeps, 
         }
       }
       __syncthreads();
+      SM_T(tC)
     }
   }
+#ifdef MGB_SMALL_TIMING
+  if (threadIdx.x == 0 && nsweeps >= 20) printf("small nz=%d nx=%d ny=%d threads=%d W=%d all_smem=%d: per colour cycles A=%lld B=%lld C=%lld\n", NZ, nx, ny, (int)blockDim.x, L.rb_W, all_smem,
+         tA / (2 * nsweeps), tB / (2 * nsweeps), tC / (2 * nsweeps));
+#endif
   if (all_smem) for (int e = threadIdx.x; e < n3; e += blockDim.x) L.p[e] = p[e];
 }
 // Fused relaxation of a MID-SIZE level without lateral neighbour ranks: all `nsweeps` red-black sweeps in ONE cooperative
@@ -1133,10 +1149,18 @@ void kernels_init() {
   cudaFuncSetAttribute(k_relax_B<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   cudaFuncSetAttribute(k_relax_B<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   cudaFuncSetAttribute(k_relax_B<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-  cudaFuncSetAttribute(k_relax_small<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-  cudaFuncSetAttribute(k_relax_small<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-  cudaFuncSetAttribute(k_relax_small<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-  cudaFuncSetAttribute(k_relax_small<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+  cudaFuncSetAttribute(k_relax_small<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+  cudaFuncSetAttribute(k_relax_small<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+  cudaFuncSetAttribute(k_relax_small<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+  cudaFuncSetAttribute(k_relax_small<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+  cudaFuncSetAttribute(k_relax_small<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+  cudaFuncSetAttribute(k_relax_small<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+  cudaFuncSetAttribute(k_relax_small<8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+  cudaFuncSetAttribute(k_relax_small<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+  cudaFuncSetAttribute(k_relax_small<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+  cudaFuncSetAttribute(k_relax_small<16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+  cudaFuncSetAttribute(k_relax_small<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+  cudaFuncSetAttribute(k_relax_small<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
 }
 bool relax_small_supported(const LevelView& L) {
   const size_t n2 = (size_t)(L.ny + 2) * (L.nx + 2);
@@ -1155,12 +1179,17 @@ void launch_relax_small(cudaStream_t st, const LevelView& L, int nsweeps, int ra
   if (all_smem == 2) smem = smem11; else if (all_smem == 1) smem = smem9;
   int threads = 64; const int ncol = L.nx * (L.ny / 2);
   while (threads < ncol && threads < 1024) threads *= 2;
+#define SMALL_CASE(NZv) \
+  if (all_smem == 2) launch_k(k_relax_small<NZv, 2>, 1, threads, smem, st, L, nsweeps, rank1); \
+  else if (all_smem == 1) launch_k(k_relax_small<NZv, 1>, 1, threads, smem, st, L, nsweeps, rank1); \
+  else launch_k(k_relax_small<NZv, 0>, 1, threads, smem, st, L, nsweeps, rank1);
   switch (L.nz) {
-    case 2: launch_k(k_relax_small<2>, 1, threads, smem, st, L, nsweeps, rank1, all_smem); break;
-    case 4: launch_k(k_relax_small<4>, 1, threads, smem, st, L, nsweeps, rank1, all_smem); break;
-    case 8: launch_k(k_relax_small<8>, 1, threads, smem, st, L, nsweeps, rank1, all_smem); break;
-    default: launch_k(k_relax_small<16>, 1, threads, smem, st, L, nsweeps, rank1, all_smem); break;
+    case 2: SMALL_CASE(2) break;
+    case 4: SMALL_CASE(4) break;
+    case 8: SMALL_CASE(8) break;
+    default: SMALL_CASE(16) break;
   }
+#undef SMALL_CASE
 }
 
 // =====================================================================================================
