@@ -122,6 +122,14 @@ int mgb_profile_level1(int reps, double* out4);
 /* Device time (us) of one fill_halo(grid(lev)%p) -- src/mg_mpi_exchange.f90:396 -- averaged over `reps` back-to-back
  * exchanges on the solver's stream (collective: every rank must call it with the same arguments). */
 int mgb_profile_halo(int lev, int reps, double* us_per_exchange);
+/* mg_tictoc (src/mg_tictoc.f90): the reference's tic/toc sites -- nhydro_solve, compute_rhs (src/nhydro.f90:67-100), solve,
+ * Fcycle (src/mg_solvers.f90:45-124), relax_3D_8_{RB,GS,FC}, residual_3D_8 (src/mg_relax.f90:128-370) -- timed per level with
+ * CUDA events.  Enabling it replaces the CUDA-graph replay of the F-cycle by plain launches (a profiling mode);
+ * MGB_TICTOC=1 in the environment enables it at mgb_init.  mgb_write_tictoc writes the table of print_tictoc
+ * (src/mg_tictoc.f90:114-153: seconds in E9.3 and call counts in I9, "Total" + one column per level) to `path`,
+ * NULL or "" = "fort.<10+rank>" like the reference. */
+int mgb_tictoc_enable(int on);
+int mgb_write_tictoc(const char* path);
 const char* mgb_version(void);
 
 #ifdef __cplusplus

@@ -996,7 +996,7 @@ __global__ void __launch_bounds__(512, 1) k_relax_mid(LevelView L, int nsweeps, 
     }
     __syncthreads();
   };
-  const double* __restrict__ b = L.b; const double* __restrict__ bet = L.bet; const double* __restrict__ g = L.g;
+  const double* __restrict__ b = L.b; const double* __restrict__ bet = L.bet;
   const double* __restrict__ c2 = L.cA[1]; const double* __restrict__ c3 = L.cA[2]; const double* __restrict__ c4 = L.cA[3];
   const double* __restrict__ c5 = L.cA[4]; const double* __restrict__ c6 = L.cA[5]; const double* __restrict__ c7 = L.cA[6];
   const double* __restrict__ c8 = L.cA[7];

@@ -114,6 +114,45 @@ struct Solver {
   int nlevs() const { return (int)L.size(); }
 };
 static Solver S;
+
+// ------------------------------------------------------------------------------------------------------
+// mg_tictoc (src/mg_tictoc.f90): the reference's eight tic/toc sites, timed with CUDA events on the solver stream.
+// Off by default (the production solve replays a CUDA graph, which has no per-operator boundaries); mgb_tictoc_enable(1)
+// or MGB_TICTOC=1 switches to plain launches and records one event pair per call.
+// ------------------------------------------------------------------------------------------------------
+struct TicToc {
+  bool on = false;
+  struct Rec { int id, lev; cudaEvent_t a, b; };
+  std::vector<Rec> open;                                      // recorded, not yet accumulated
+  std::vector<std::string> names;                             // in order of first tic, like the reference's subname(:)
+  std::vector<std::vector<double>> time;                      // [id][lev-1] seconds
+  std::vector<std::vector<long long>> calls;
+};
+static TicToc T;
+static int tt_tic(const char* name, int lev) {
+  if (!T.on) return -1;
+  int id = -1;
+  for (size_t q = 0; q < T.names.size(); ++q) if (T.names[q] == name) id = (int)q;
+  if (id < 0) { id = (int)T.names.size(); T.names.push_back(name); T.time.emplace_back(S.nlevs(), 0.0); T.calls.emplace_back(S.nlevs(), 0); }
+  TicToc::Rec r{id, lev, nullptr, nullptr};
+  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return -1;
+  cudaEventRecord(r.a, S.st);
+  T.open.push_back(r);
+  return (int)T.open.size() - 1;
+}
+static void tt_toc(int h) { if (h >= 0 && h < (int)T.open.size()) cudaEventRecord(T.open[h].b, S.st); }
+static void tt_flush() {
+  if (T.open.empty()) return;
+  cudaStreamSynchronize(S.st);
+  for (auto& r : T.open) {
+    float ms = 0; cudaEventElapsedTime(&ms, r.a, r.b);
+    if (r.lev >= 1 && r.lev <= (int)T.time[r.id].size()) { T.time[r.id][r.lev - 1] += 1e-3 * ms; T.calls[r.id][r.lev - 1] += 1; }
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  T.open.clear();
+}
+static void tt_reset() { tt_flush(); T.names.clear(); T.time.clear(); T.calls.clear(); }
+struct TicGuard { int h; TicGuard(const char* n, int lev) : h(tt_tic(n, lev)) {} ~TicGuard() { tt_toc(h); } };
 static Params g_params;              // defaults + mgb_set_param overrides (used by mgb_plan_levels)
 static std::vector<std::pair<std::string, std::string>> g_overrides;   // applied after the namelist file in mgb_init
 static std::vector<LevelDims> g_plan;
@@ -257,6 +296,7 @@ static int gather(int lev, const double* x, double* y, int nzl) {
 static int relax(int lev, int nsweeps) {
   Level& g = S.L[lev - 1];
   const std::string& m = S.P.relax_method;
+  TicGuard tg(m == "Red-Black" || m == "RB" ? "relax_3D_8_RB" : (m == "Four-Color" || m == "FC" ? "relax_3D_8_FC" : "relax_3D_8_GS"), lev);   // src/mg_relax.f90:128,167,209
   const bool real_matrix = (S.P.cmatrix == "real");
   if (m == "Red-Black" || m == "RB") {
     bool lonely = true; for (int q = 0; q < 8; ++q) lonely &= g.d.neighb[q] < 0;
@@ -320,7 +360,8 @@ static int relax(int lev, int nsweeps) {
 // r = b - A p, halo(r); the sum of squares of this rank is left in S.sums[0]
 static int residual(int lev) {
   Level& g = S.L[lev - 1];
-  launch_residual(S.st, g.v, S.P.cmatrix == "real", g.partials, S.sums);
+  { TicGuard tg("residual_3D_8", lev);                        // src/mg_relax.f90:367-370
+    launch_residual(S.st, g.v, S.P.cmatrix == "real", g.partials, S.sums); }
   RC(fill_halo(lev, g.v.r, g.d.nz, 1));
   return 0;
 }
@@ -380,6 +421,7 @@ static int vcycle(int lev1) {
   return 0;
 }
 static int fcycle() {
+  TicGuard tg("Fcycle", 1);                                   // src/mg_solvers.f90:108,124
   const int Ln = S.nlevs();
   for (int lev = 1; lev <= Ln - 1; ++lev) RC(fine2coarse(lev, true));
   RC(relax(Ln, S.P.ns_coarsest));
@@ -413,6 +455,7 @@ static int solve_p() {
   const double tol = S.P.solver_prec; const int maxite = S.P.solver_maxiter;
   launch_fill(S.st, g.v.p, 0.0, g.n3());
   CU(cudaEventRecord(S.ev0, S.st));
+  TicGuard tg_solve("solve", 1);                              // src/mg_solvers.f90:45,82
   int nite = 0;
   launch_sumsq(S.st, g.v, g.v.b, g.partials, S.sums + 1);
   double bsum = 0, rsum = 0;
@@ -423,7 +466,7 @@ static int solve_p() {
   double res0 = rnorm / bnorm;
   S.hist_res.assign(1, res0); S.hist_conv.assign(1, 0.0);
   while (nite < maxite && res0 > tol) {
-    if (S.use_graph) {
+    if (S.use_graph && !T.on) {
       if (!S.cycle_graph) RC(build_cycle_graph());
       CU(cudaGraphLaunch(S.cycle_graph, S.st));
       g_launches += S.cycle_graph_nodes;
@@ -614,6 +657,7 @@ static int correct_uvw_device() {
 // ------------------------------------------------------------------------------------------------------
 static int clean() {
   if (S.st) cudaStreamSynchronize(S.st);
+  tt_reset();
   drop_cycle_graph();
   for (void* p : S.peer_mbox) if (p) cudaIpcCloseMemHandle(p);
   if (S.p2p_err_host) cudaFreeHost(S.p2p_err_host);
@@ -693,6 +737,7 @@ static int init(int nx, int ny, int nz, int npx, int npy, int rank, const char* 
   S.fuse_halo = !(nf && nf[0] == '1');
   const char* nb = std::getenv("MGB_NO_FUSED_BC");
   S.fuse_bc = !(nb && nb[0] == '1');
+  { const char* tt = std::getenv("MGB_TICTOC"); T = TicToc(); T.on = tt && tt[0] == '1'; }
   const char* ng = std::getenv("MGB_NO_GRAPH");
   S.use_graph = !(ng && ng[0] == '1');
   kernels_init();
@@ -901,9 +946,48 @@ int mgb_correct_uvw(double* u, double* v, double* w) {
 }
 int mgb_solve(const double* rmask, double* u, double* v, double* w) {
   if (!S.have_matrices) return fail("mgb_matrices has not been called");
-  RC(set_rmask(rmask)); RC(upload_uvw(u, v, w)); RC(compute_rhs_device());
+  TicGuard tg("nhydro_solve", 1);                             // src/nhydro.f90:67,100
+  RC(set_rmask(rmask)); RC(upload_uvw(u, v, w));
+  { TicGuard tr("compute_rhs", 1); RC(compute_rhs_device()); }   // src/nhydro.f90:81-83
   RC(solve_p());
   RC(correct_uvw_device()); return download_uvw(u, v, w);
+}
+
+int mgb_tictoc_enable(int on) {
+  if (!S.inited) return fail("mgb_init has not been called");
+  tt_reset();
+  T.on = on != 0;
+  return 0;
+}
+// print_tictoc (src/mg_tictoc.f90:114-153): per timer one line of seconds (Total + one column per level, E9.3) and one of calls (I9)
+int mgb_write_tictoc(const char* path) {
+  if (!S.inited) return fail("mgb_init has not been called");
+  tt_flush();
+  char def[32]; std::snprintf(def, sizeof def, "fort.%d", 10 + S.rank);
+  FILE* f = std::fopen((path && path[0]) ? path : def, "w");
+  if (!f) return fail("cannot open the tictoc file");
+  auto e93 = [](double v, char* out) {       // Fortran E9.3: 0.dddE+xx
+    if (v == 0.0) { std::snprintf(out, 32, "0.000E+00"); return; }
+    int ex = (int)std::floor(std::log10(std::fabs(v))) + 1;
+    double m = v / std::pow(10.0, ex);
+    if (std::fabs(m) >= 0.9995) { m /= 10.0; ++ex; }
+    std::snprintf(out, 32, "%.3fE%c%02d", m, ex < 0 ? '-' : '+', std::abs(ex) % 100);
+  };
+  const int nl = S.nlevs(); char buf[32];
+  std::fprintf(f, "%21s%10s", "", "Total");
+  for (int l = 1; l <= nl; ++l) std::fprintf(f, " %9d", l);
+  std::fprintf(f, " \n");
+  for (size_t q = 0; q < T.names.size(); ++q) {
+    double tot = 0; long long ctot = 0;
+    for (int l = 0; l < nl; ++l) { tot += T.time[q][l]; ctot += T.calls[q][l]; }
+    e93(tot, buf); std::fprintf(f, " %20s %s", T.names[q].c_str(), buf);
+    for (int l = 0; l < nl; ++l) { e93(T.time[q][l], buf); std::fprintf(f, " %s", buf); }
+    std::fprintf(f, " \n%21s %9lld", "", ctot);
+    for (int l = 0; l < nl; ++l) std::fprintf(f, " %9lld", T.calls[q][l]);
+    std::fprintf(f, " \n");
+  }
+  std::fclose(f);
+  return 0;
 }
 
 int mgb_get_history(double* res, double* conv, int cap) {

@@ -75,6 +75,8 @@ def load(build_if_missing: bool = True):
     L.mgb_reset_launch_count.restype = None
     L.mgb_profile_level1.argtypes = [C.c_int, _dp]
     L.mgb_profile_halo.argtypes = [C.c_int, C.c_int, _dp]
+    L.mgb_tictoc_enable.argtypes = [C.c_int]
+    L.mgb_write_tictoc.argtypes = [C.c_char_p]
     _lib = L
     return L
 
@@ -199,6 +201,17 @@ def profile_level1(reps=10):
     out = (C.c_double * 4)()
     _chk(load().mgb_profile_level1(reps, out))
     return dict(relax_colour_ms=out[0], residual_ms=out[1], restrict_ms=out[2], prolong_ms=out[3])
+
+
+def tictoc_enable(on=True): _chk(load().mgb_tictoc_enable(1 if on else 0))
+def write_tictoc(path=None): _chk(load().mgb_write_tictoc((path or "").encode()))
+
+
+def dump_field(name, lev=1, path=None):
+    """Field dump replacing the reference's write_netcdf debug output (src/mg_netcdf_out.f90): grid(lev)%<name> as .npy."""
+    a = get_field(name, lev)
+    np.save(path or f"{name}_lev{lev}.npy", a)
+    return a
 
 
 def profile_halo(lev, reps=100):

@@ -274,3 +274,35 @@ def test_bmask_nhydro_solve_end_to_end(nh):
     bn = nh.get_field("b")[1:-1, 1:-1]
     o2 = make_oracle("seamount", nx, ny, nz, uvw="random", **prm); o2.compute_rhs()
     assert np.abs(bn[:, :, :-2]).max() < 1e-7 * np.abs(o2.get("b")[1:-1, 1:-1]).max()
+
+
+def test_tictoc_table_and_field_dump(nh, tmp_path):
+    """mg_tictoc (src/mg_tictoc.f90:114-153): the per-level table of the reference's tic/toc sites, and a .npy field dump in
+    place of the NetCDF debug output.  The profiling mode (plain launches instead of the graph) must not change the result."""
+    nx, ny, nz = 32, 32, 16
+    prm = dict(solver_prec=1e-10, solver_maxiter=20)
+    make_product(nh, "seamount", nx, ny, nz, **prm)
+    u, v, w = velocities("wminus1", nx, ny, nz)
+    nh.nhydro_solve(nx, ny, nz, None, u.copy(), v.copy(), w.copy())
+    h_graph = nh.history()[0]
+    nh.tictoc_enable(True)
+    nh.nhydro_solve(nx, ny, nz, None, u.copy(), v.copy(), w.copy())
+    assert np.array_equal(nh.history()[0], h_graph)
+    path = tmp_path / "fort.10"
+    nh.write_tictoc(str(path))
+    lines = path.read_text().splitlines()
+    nl = nh.nlevs(); ncyc = len(h_graph) - 1
+    assert lines[0].split() == ["Total"] + [str(l) for l in range(1, nl + 1)]
+    rows = {lines[q].split()[0]: (lines[q].split()[1:], lines[q + 1].split()) for q in range(1, len(lines), 2)}
+    assert list(rows) == ["nhydro_solve", "compute_rhs", "solve", "residual_3D_8", "Fcycle", "relax_3D_8_RB"]
+    times, calls = rows["relax_3D_8_RB"]
+    assert len(times) == nl + 1 and all(len(t) == 9 and "E" in t for t in times)
+    # one F-cycle relaxes level l twice per V-cycle that reaches it (l V-cycles for l < nl) and the coarsest level once per V-cycle + once
+    want = [2 * l * ncyc for l in range(1, nl)] + [nl * ncyc]
+    assert [int(c) for c in calls[1:]] == want and int(calls[0]) == sum(want)
+    assert int(rows["Fcycle"][1][0]) == ncyc and int(rows["solve"][1][0]) == 1 and int(rows["nhydro_solve"][1][0]) == 1
+    assert int(rows["residual_3D_8"][1][1]) == 2 * ncyc + 1      # per cycle: the V-cycle at level 1 + the convergence check; + the initial one
+    assert abs(float(rows["solve"][0][0]) - 1e-3 * nh.last_solve_ms()) < 0.2 * float(rows["solve"][0][0])
+    nh.tictoc_enable(False)
+    a = nh.dump_field("p", 1, str(tmp_path / "p.npy"))
+    assert np.array_equal(np.load(tmp_path / "p.npy"), a)
