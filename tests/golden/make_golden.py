@@ -20,6 +20,9 @@ CASES = [
     dict(name="rndtopo 32x32x16 2x2", kind="rndtopo", local=[16, 16, 16], npx=2, npy=2, params=dict(solver_prec=1e-10)),
     dict(name="cuc 32x16x8 2x1 gathered", kind="cuc", local=[16, 16, 8], npx=2, npy=1, params=dict(solver_prec=1e-10, nsmall=16)),
     dict(name="seamount 16^3 FC nearest", kind="seamount", local=[16, 16, 16], npx=1, npy=1, params=dict(solver_prec=1e-8, relax_method="FC", interp_type="nearest")),
+    dict(name="seamount 32x16x16 GS", kind="seamount", local=[32, 16, 16], npx=1, npy=1, params=dict(solver_prec=1e-9, relax_method="GS")),
+    dict(name="seamount 32x32x16 bmask", kind="seamount", local=[32, 32, 16], npx=1, npy=1, params=dict(solver_prec=1e-10, bmask=True)),
+    dict(name="rndtopo 32x32x16 2x2 bmask", kind="rndtopo", local=[16, 16, 16], npx=2, npy=2, params=dict(solver_prec=1e-10, bmask=True)),
 ]
 out = {"generator": "tests/golden/make_golden.py (CPU oracle, -ffp-contract=off)", "cases": []}
 for c in CASES:

@@ -306,3 +306,26 @@ def test_tictoc_table_and_field_dump(nh, tmp_path):
     nh.tictoc_enable(False)
     a = nh.dump_field("p", 1, str(tmp_path / "p.npy"))
     assert np.array_equal(np.load(tmp_path / "p.npy"), a)
+
+
+def test_committed_golden_fixtures_single_rank(nh):
+    """The CUDA path against the committed fixtures of tests/golden/ (oracle-generated, see make_golden.py): every single-rank
+    case, history to 1e-10 relative and the sum of |p| to 1e-9."""
+    import json, os
+    from mgroms_b200 import testcases as tc
+    with open(os.path.join(os.path.dirname(__file__), "golden", "oracle_histories.json")) as f:
+        gold = json.load(f)
+    done = 0
+    for case in gold["cases"]:
+        if case["npx"] * case["npy"] != 1:
+            continue
+        nx, ny, nz = case["local"]
+        prm = dict(case["params"])
+        make_product(nh, case["kind"], nx, ny, nz, **prm)
+        rm = tc.bmask_rmask(nx, ny) if prm.get("bmask") else None
+        nh.compute_rhs(rm, *velocities("wminus1", nx, ny, nz)); nh.solve_p()
+        history_close(nh.history()[0], np.array(case["history"]), rtol=1e-10, floor=2e-15)
+        s = float(np.abs(nh.get_field("p")).sum())
+        assert abs(s - case["p_abs_sum"]) <= 1e-9 * case["p_abs_sum"], case["name"]
+        done += 1
+    assert done >= 5
