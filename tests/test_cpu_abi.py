@@ -137,3 +137,15 @@ def test_compute_fails_loudly_without_gpu(nh):
         nh.nhydro_init(16, 16, 16)
     with pytest.raises(nh.MgbError):
         nh.solve_p()
+
+
+@pytest.mark.skipif(has_gpu(), reason="checks the no-GPU failure mode")
+def test_plain_c_driver_builds_and_fails_loudly_without_gpu(tmp_path):
+    """examples/mg_testseamount.c compiles against include/mgb.h + libmgb.so with gcc alone and, without a device, stops with the
+    library's message (the reference `stop`s) instead of computing anything on the CPU."""
+    import subprocess
+    import __graft_entry__ as ge
+    ge.build()
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "mg_testseamount")
+    out = subprocess.run([exe, "16", "16", "16"], cwd=tmp_path, capture_output=True, text=True, timeout=120)
+    assert out.returncode != 0 and "no usable CUDA device" in out.stderr

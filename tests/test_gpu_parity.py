@@ -329,3 +329,21 @@ def test_committed_golden_fixtures_single_rank(nh):
         assert abs(s - case["p_abs_sum"]) <= 1e-9 * case["p_abs_sum"], case["name"]
         done += 1
     assert done >= 5
+
+
+def test_plain_c_driver_over_the_abi(nh, tmp_path):
+    """examples/mg_testseamount.c (C only, mirrors src/mg_testseamount.f90) links libmgb.so and reproduces the history the
+    Python mirror gets for the same case (geometry evaluated with libm's exp instead of NumPy's: agreement to 1e-9)."""
+    import os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "examples", "mg_testseamount")
+    if not os.path.exists(exe):
+        import __graft_entry__ as ge
+        ge.build()
+    out = subprocess.run([exe, "32", "32", "32"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    hist_c = np.array([float(l.split()[0]) for l in (tmp_path / "fort.100").read_text().splitlines() if l.strip()])
+    make_product(nh, "seamount", 32, 32, 32, solver_prec=1e-10)
+    nh.compute_rhs(None, *velocities("wminus1", 32, 32, 32)); nh.solve_p()
+    history_close(hist_c, nh.history()[0], rtol=1e-9, floor=1e-15)
+    assert "max |div| after the correction" in out.stdout
