@@ -109,6 +109,7 @@ struct Solver {
   bool use_graph = true;             // replay one captured F-cycle (+ residual) per outer iteration
   bool fuse_halo = true;             // neighbour-free levels: relax kernels write the Neumann halo themselves
   bool fuse_bc = true;               // neighbour-free levels: kernels B and C fused
+  size_t fuse_bc_limit = 3000000;    // ... up to this many points (larger levels stream better with the separate C)
   cudaGraphExec_t cycle_graph = nullptr;
   long long cycle_graph_nodes = 0;
   int nlevs() const { return (int)L.size(); }
@@ -311,7 +312,7 @@ static int relax(int lev, int nsweeps) {
     const bool rank1 = real_matrix && g.bottom_diag;
     const int fuse = (lonely && S.fuse_halo) ? 1 : 0;
     // B+C fused: chunked recurrence only, and only where the level is latency-bound (the separate C streams better on big levels)
-    const bool fuse_bc = fuse && rank1 && S.fuse_bc && g.v.rb_chunk < g.d.nx && g.n3() <= (size_t)3000000;
+    const bool fuse_bc = fuse && rank1 && S.fuse_bc && g.v.rb_chunk < g.d.nx && g.n3() <= S.fuse_bc_limit;
     const int xmode = fuse ? 1 : 2;                           // 2: neighbours -> C keeps x1's interior, the exchange its halo ring
     if (rank1) launch_snapshot_x1(S.st, g.v);                 // x1 = p(1,:,:) once per call; kept current afterwards
     LevelView v = g.v;
@@ -737,6 +738,7 @@ static int init(int nx, int ny, int nz, int npx, int npy, int rank, const char* 
   S.fuse_halo = !(nf && nf[0] == '1');
   const char* nb = std::getenv("MGB_NO_FUSED_BC");
   S.fuse_bc = !(nb && nb[0] == '1');
+  { const char* fl = std::getenv("MGB_FUSE_BC_LIMIT"); if (fl) S.fuse_bc_limit = (size_t)std::atoll(fl); }
   { const char* tt = std::getenv("MGB_TICTOC"); T = TicToc(); T.on = tt && tt[0] == '1'; }
   const char* ng = std::getenv("MGB_NO_GRAPH");
   S.use_graph = !(ng && ng[0] == '1');
