@@ -73,9 +73,12 @@ void launch_sumsq(cudaStream_t st, const LevelView& L, const double* a, double* 
 // ---- intergrid (src/mg_intergrids.f90) -------------------------------------------------------------------
 // y_c(k2,j2,i2) = sum of the 8 fine cells of x_f ; y has local dims (nxc,nyc,nzc) with 1 halo
 void launch_restrict8(cudaStream_t st, const double* xf, int nzf, int nyf, int nxf, double* yc, int nzc, int nyc, int nxc);
+// the same on a neighbour-free coarse level, fused with halo(y_c), p_c = 0 (whole array) and, when rc != nullptr, r_c = y_c
+void launch_restrict8_fused(cudaStream_t st, const double* xf, int nzf, int nyf, int nxf, double* yc, double* pc, double* rc, int nzc, int nyc, int nxc);
 // trilinear/nearest prolongation of xc (nzc,nyc,nxc) onto the fine interior.
 // mode 0: rf = interp           (reference's first step; halo(rf) and p+=rf done by the caller)
 // mode 1: pf += interp          (fused; caller refreshes halo(pf))
+// mode 2: as mode 1 on a neighbour-free fine level: the kernel writes the Neumann halo of pf itself (linear only)
 void launch_prolong(cudaStream_t st, const double* xc, int nzc, int nyc, int nxc, double* rf, double* pf, int linear, int mode);
 void launch_axpy_all(cudaStream_t st, double* y, const double* x, size_t n);          // y += x
 void launch_add_halo_ring(cudaStream_t st, double* p, const double* r, int nz, int ny, int nx);  // p += r on the halo ring only

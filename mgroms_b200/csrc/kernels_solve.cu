@@ -1343,6 +1343,36 @@ void launch_restrict8(cudaStream_t st, const double* xf, int nzf, int nyf, int n
   launch_k(k_restrict8, blocks_for(n, 256), 256, 0, st, xf, nzf, nyf, yc, nzc, nyc, nxc);
 }
 
+// fine2coarse of a neighbour-free coarse level in ONE launch: b_c = restriction with its Neumann halo, p_c = 0 everywhere and
+// (F-cycle descent) r_c = b_c -- what restrict + fill_halo + fill + copy do in four (src/mg_intergrids.f90:16-72, src/mg_solvers.f90:113-118)
+__global__ void __launch_bounds__(256) k_restrict8_fused(const double* __restrict__ xf, int nzf, int nyf, double* __restrict__ yc, double* __restrict__ pc,
+                                                         double* __restrict__ rc, int nzc, int nyc, int nxc) {
+  const int n = nzc * nyc * nxc;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const int t = e / nzc, k2 = e - t * nzc;
+  const int i2 = 1 + t / nyc, j2 = 1 + (t - (i2 - 1) * nyc);
+  const int k = 2 * k2, j = 2 * j2 - 1, i = 2 * i2 - 1;       // k 0-based
+  const int nyf2 = nyf + 2;
+  const int sj = nzf, si = nzf * nyf2;
+  const int f00 = k + nzf * (j + nyf2 * i);
+  const double2 a = *reinterpret_cast<const double2*>(xf + f00);             // (k, k+1) at (j, i)
+  const double2 b = *reinterpret_cast<const double2*>(xf + f00 + si);        // (j, i+1)
+  const double2 c = *reinterpret_cast<const double2*>(xf + f00 + sj);        // (j+1, i)
+  const double2 d = *reinterpret_cast<const double2*>(xf + f00 + sj + si);   // (j+1, i+1)
+  const double z = a.x + b.x + c.x + d.x + a.y + b.y + c.y + d.y;
+  const size_t o = (size_t)(k2 + nzc * (j2 + (nyc + 2) * i2));
+  const size_t csj = nzc, csi = (size_t)nzc * (nyc + 2);
+  store_mirrored(yc, o, z, j2, i2, nyc, nxc, csj, csi, true);
+  store_mirrored(pc, o, 0.0, j2, i2, nyc, nxc, csj, csi, true);
+  if (rc) store_mirrored(rc, o, z, j2, i2, nyc, nxc, csj, csi, true);
+}
+void launch_restrict8_fused(cudaStream_t st, const double* xf, int nzf, int nyf, int nxf, double* yc, double* pc, double* rc, int nzc, int nyc, int nxc) {
+  (void)nxf;
+  size_t n = (size_t)nzc * nyc * nxc;
+  launch_k(k_restrict8_fused, blocks_for(n, 256), 256, 0, st, xf, nzf, nyf, yc, pc, rc, nzc, nyc, nxc);
+}
+
 // prolongation (src/mg_intergrids.f90:366-450 linear, :336-363 nearest); thread per fine interior point
 __global__ void __launch_bounds__(256) k_prolong(const double* __restrict__ xc, int nzc, int nyc, int nxc,
                                                 double* __restrict__ rf, double* __restrict__ pf, int linear, int mode) {
@@ -1381,8 +1411,10 @@ __global__ void __launch_bounds__(256) k_prolong(const double* __restrict__ xc, 
 // thread per COARSE interior point: computes its 8 fine children from the 27 surrounding coarse values (each child with
 // exactly the expression of the reference, see k_prolong) and writes them as (k,k+1) double2 pairs: 27 cached loads
 // per 8 fine points instead of 64, and 16-byte coalesced read-modify-write of p.
+// mode 2 = mode 1 (pf += interp) on a neighbour-free fine level: the Neumann halo of pf is written too (no fill_halo launch)
+template <int mode>
 __global__ void __launch_bounds__(256, 3) k_prolong8(const double* __restrict__ xc, int nzc, int nyc, int nxc,
-                                                 double* __restrict__ rf, double* __restrict__ pf, int mode) {
+                                                 double* __restrict__ rf, double* __restrict__ pf) {
   const int n = nzc * nyc * nxc;                                              // 32-bit element indices throughout
   const int e_raw = blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = e_raw < n;
@@ -1398,7 +1430,7 @@ __global__ void __launch_bounds__(256, 3) k_prolong8(const double* __restrict__ 
   for (int q = 0; q < 4; ++q) {
     const int jf = 2 * j2 - 1 + (q >> 1), i_f = 2 * i2 - 1 + (q & 1);
     of[q] = 2 * (k2 - 1) + nzf * (jf + nyf2 * i_f);
-    pv[q] = (mode == 0) ? make_double2(0.0, 0.0) : *reinterpret_cast<const double2*>(pf + of[q]);
+    pv[q] = (mode == 0) ? make_double2(0.0, 0.0) : *reinterpret_cast<const double2*>(pf + of[q]);   // modes 1, 2
   }
   // coarse value at (k2, j2+dj, i2+di) and its vertical neighbours: the levels k2-1 / k2+1 of the same column sit in the
   // adjacent lanes (k2 is the fastest index), so they travel by shuffle; only a warp-boundary lane loads them
@@ -1432,14 +1464,32 @@ __global__ void __launch_bounds__(256, 3) k_prolong8(const double* __restrict__ 
              vhi = d * x00 + f * xdd + ee * xd0 + ee * x0d + ee * y00 + g * ydd + f * yd0 + f * y0d; }
       if (!valid) continue;
       if (mode == 0) *reinterpret_cast<double2*>(rf + of[q]) = make_double2(vlo, vhi);
-      else *reinterpret_cast<double2*>(pf + of[q]) = make_double2(pv[q].x + vlo, pv[q].y + vhi);
+      else {
+        const double2 v = make_double2(pv[q].x + vlo, pv[q].y + vhi);
+        *reinterpret_cast<double2*>(pf + of[q]) = v;
+        if (mode == 2) {      // mirrors of an edge / corner fine column (16-byte aligned: nzf is even)
+          const int jf = 2 * j2 - 1 + cj, i_f = 2 * i2 - 1 + ci, nyf = 2 * nyc, nxf = 2 * nxc;
+          const int sj = nzf, si = nzf * nyf2;
+          const bool w = (i_f == 1), ea = (i_f == nxf), so = (jf == 1), no = (jf == nyf);
+          if (w) *reinterpret_cast<double2*>(pf + of[q] - si) = v;
+          if (ea) *reinterpret_cast<double2*>(pf + of[q] + si) = v;
+          if (so) *reinterpret_cast<double2*>(pf + of[q] - sj) = v;
+          if (no) *reinterpret_cast<double2*>(pf + of[q] + sj) = v;
+          if (w && so) *reinterpret_cast<double2*>(pf + of[q] - si - sj) = v;
+          if (w && no) *reinterpret_cast<double2*>(pf + of[q] - si + sj) = v;
+          if (ea && so) *reinterpret_cast<double2*>(pf + of[q] + si - sj) = v;
+          if (ea && no) *reinterpret_cast<double2*>(pf + of[q] + si + sj) = v;
+        }
+      }
     }
   }
 }
 void launch_prolong(cudaStream_t st, const double* xc, int nzc, int nyc, int nxc, double* rf, double* pf, int linear, int mode) {
   if (linear) {
     size_t n = (size_t)nzc * nyc * nxc;
-    launch_k(k_prolong8, blocks_for(n, 256), 256, 0, st, xc, nzc, nyc, nxc, rf, pf, mode);
+    if (mode == 0) launch_k(k_prolong8<0>, blocks_for(n, 256), 256, 0, st, xc, nzc, nyc, nxc, rf, pf);
+    else if (mode == 1) launch_k(k_prolong8<1>, blocks_for(n, 256), 256, 0, st, xc, nzc, nyc, nxc, rf, pf);
+    else launch_k(k_prolong8<2>, blocks_for(n, 256), 256, 0, st, xc, nzc, nyc, nxc, rf, pf);
     return;
   }
   size_t n = (size_t)8 * nzc * nyc * nxc;

@@ -385,6 +385,11 @@ static int global_sum(int lev, const double* dev_local, double* out) {
 static int fine2coarse(int lev, bool copy_b_to_r) {
   Level& f = S.L[lev - 1]; Level& c = S.L[lev];
   const int nxs = c.d.nx / c.d.ngx, nys = c.d.ny / c.d.ngy;
+  bool lonely = true; for (int q = 0; q < 8; ++q) lonely &= c.d.neighb[q] < 0;
+  if (lonely && !c.d.gather && S.fuse_halo) {                  // one launch: restriction + halo(b_c) + p_c = 0 (+ r_c = b_c)
+    launch_restrict8_fused(S.st, f.v.r, f.d.nz, f.d.ny, f.d.nx, c.v.b, c.v.p, copy_b_to_r ? c.v.r : nullptr, c.d.nz, c.d.ny, c.d.nx);
+    return 0;
+  }
   double* target = c.d.gather ? c.dummy3 : c.v.b;
   launch_restrict8(S.st, f.v.r, f.d.nz, f.d.ny, f.d.nx, target, c.d.nz, nys, nxs);
   if (c.d.gather) RC(gather(lev + 1, c.dummy3, c.v.b, c.d.nz));
@@ -404,6 +409,8 @@ static int coarse2fine(int lev, bool fused) {
   }
   const int linear = (S.P.interp_type == "linear");
   if (fused) {   // p_f += P p_c on the interior, then refresh halo(p_f): identical to the reference whenever halo(p_f) was consistent
+    bool lonely = true; for (int q = 0; q < 8; ++q) lonely &= f.d.neighb[q] < 0;
+    if (lonely && linear && S.fuse_halo && f.n3() <= (size_t)3000000) { launch_prolong(S.st, pc, c.d.nz, nyc, nxc, f.v.r, f.v.p, linear, 2); return 0; }   // latency-bound levels: halo written by the kernel (on big levels the mirror code costs more than the launch)
     launch_prolong(S.st, pc, c.d.nz, nyc, nxc, f.v.r, f.v.p, linear, 1);
     RC(fill_halo(lev, f.v.p, f.d.nz, 1));
   } else {       // the reference's sequence: r_f = P p_c ; halo(r_f) ; p_f += r_f everywhere
@@ -1120,7 +1127,7 @@ int mgb_profile_level1(int reps, double* out4) {
     for (int pass = 0; pass < 2; ++pass) {
       const int n = pass == 0 ? 2 : reps;
       CU(cudaEventRecord(a, S.st));
-      for (int r = 0; r < n; ++r) { launch_restrict8(S.st, g.v.r, g.d.nz, g.d.ny, g.d.nx, c.v.b, c.d.nz, c.d.ny, c.d.nx); RC(fill_halo(2, c.v.b, c.d.nz, 1)); launch_fill(S.st, c.v.p, 0.0, c.n3()); }
+      for (int r = 0; r < n; ++r) RC(fine2coarse(1, false));
       CU(cudaEventRecord(b, S.st)); CU(cudaEventSynchronize(b)); CU(cudaEventElapsedTime(&ms, a, b));
       out4[2] = ms / n;
     }
