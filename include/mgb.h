@@ -112,9 +112,16 @@ int mgb_set_field(int lev, const char* name, const double* in);
 
 /* ---- diagnostics ----------------------------------------------------------------------------- */
 const char* mgb_last_error(void);
+/* Transport of the nh = 1 halo exchange (replaces the Isend/Irecv pairs of src/mg_mpi_exchange.f90:396-745):
+ * 0 = single rank (no communicator), 1 = NVLink peer-memory mailboxes, 2 = NCCL send/recv (fallback, or MGB_NO_P2P=1). */
+int mgb_halo_transport(void);
 /* Kernel launches issued by this library since the last mgb_reset_launch_count() (bench.py's gpu_launches). */
 long long mgb_launch_count(void);
 void mgb_reset_launch_count(void);
+/* Which kernels relax(lev, .) runs for this level and configuration: "small" (single CTA), "mid" (cooperative launch),
+ * "fused" (one persistent launch per colour), "a+bc" / "a+b+c" (separate launches), "a" (no k=1 diagonal coupling),
+ * suffixed "+halo" / "+exchange" when the halo fill is a separate launch.  Diagnostic for tests and bench.py. */
+int mgb_relax_path(int lev, char* out, int cap);
 /* Per-kernel-class device time accumulated by mgb_profile_level1(): runs `reps` launches of each level-1
  * hot kernel on the current state and reports average ms per launch.
  * out[0]=relax colour (all launches of one colour), [1]=residual+norm, [2]=restrict, [3]=prolong+add. */

@@ -1,6 +1,8 @@
 """Builds libmgb.so (the CUDA product library) in-tree with nvcc for sm_100a.
 
     python -m mgroms_b200.build [--force] [--verbose]
+
+Every translation unit is compiled to an object file in parallel (only the ones whose sources changed), then linked.
 """
 from __future__ import annotations
 
@@ -8,12 +10,14 @@ import os
 import shutil
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "obj")
 SO = os.path.join(HERE, "libmgb.so")
-SOURCES = ["host_plan.cpp", "kernels_solve.cu", "kernels_setup.cu", "solver.cu"]
-HEADERS = ["mgb_internal.h", "kernels.cuh", os.path.join("..", "..", "include", "mgb.h")]
+SOURCES = ["host_plan.cpp", "kernels_solve.cu", "kernels_relax.cu", "kernels_setup.cu", "solver.cu"]
+HEADERS = ["mgb_internal.h", "kernels.cuh", "device_utils.cuh", os.path.join("..", "..", "include", "mgb.h")]
 
 
 def nvcc_path() -> str:
@@ -21,6 +25,10 @@ def nvcc_path() -> str:
         if cand and os.path.exists(cand):
             return cand
     raise RuntimeError("nvcc not found")
+
+
+def _newest_header() -> float:
+    return max(os.path.getmtime(os.path.join(CSRC, h)) for h in HEADERS + [os.path.join("..", "build.py")])
 
 
 def needs_build() -> bool:
@@ -34,16 +42,30 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return SO
+    os.makedirs(OBJ, exist_ok=True)
     ccbin = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-fmad=false", "-Xcompiler", "-fPIC", "-shared", "-ccbin", ccbin,
-           "-o", SO] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
+    base = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+            "-fmad=false", "-Xcompiler", "-fPIC", "-ccbin", ccbin]
     if os.environ.get("MGB_BUILD_DEFS"):
-        cmd[1:1] = ["-D" + d for d in os.environ["MGB_BUILD_DEFS"].split(",")]
+        base += ["-D" + d for d in os.environ["MGB_BUILD_DEFS"].split(",")]
+        force = True
     if verbose:
-        cmd.insert(1, "-Xptxas"); cmd.insert(2, "-v")
-        print(" ".join(cmd))
-    subprocess.check_call(cmd)
+        base += ["-Xptxas", "-v"]
+    hdr_t = _newest_header()
+
+    def compile_one(src: str) -> str:
+        obj = os.path.join(OBJ, os.path.splitext(src)[0] + ".o")
+        path = os.path.join(CSRC, src)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(path), hdr_t):
+            cmd = base + ["-c", path, "-o", obj]
+            if verbose:
+                print(" ".join(cmd))
+            subprocess.check_call(cmd)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    subprocess.check_call([nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-ccbin", ccbin, "-o", SO] + objs + ["-ldl"])
     return SO
 
 

@@ -1,0 +1,62 @@
+// device_utils.cuh -- helpers shared by the kernel translation units (kernels_solve.cu, kernels_relax.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include "kernels.cuh"
+
+namespace mgb {
+
+#define IDX3(k, j, i, nzl, ny2) ((size_t)(k) + (size_t)(nzl) * ((size_t)(j) + (size_t)(ny2) * (size_t)(i)))
+
+static inline unsigned blocks_for(size_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
+
+// one launch path for every kernel (counts the launches for mgb_launch_count; the first failing launch is remembered
+// and surfaced by the next API boundary, see note_launch_error)
+template <typename... KArgs, typename... Args>
+static void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  note_launch_error(cudaLaunchKernelEx(&cfg, kern, KArgs(args)...));
+  ++g_launches;
+}
+
+// Store a freshly relaxed value and, on a level without lateral neighbour ranks, its homogeneous-Neumann mirror(s):
+// the halo cell next to an edge column (and the corner next to a corner column) takes the same value, which is what
+// fill_halo would copy afterwards (src/mg_mpi_exchange.f90:504-598).  Saves the separate halo launch per colour.
+template <typename T>
+__device__ __forceinline__ void store_mirrored_t(T* __restrict__ a, size_t idx, T v, int j, int i, int ny, int nx, size_t sj, size_t si, bool mirror) {
+  a[idx] = v;
+  if (!mirror) return;
+  const bool w = (i == 1), e = (i == nx), s = (j == 1), n = (j == ny);
+  if (w) a[idx - si] = v;
+  if (e) a[idx + si] = v;
+  if (s) a[idx - sj] = v;
+  if (n) a[idx + sj] = v;
+  if (w && s) a[idx - si - sj] = v;
+  if (w && n) a[idx - si + sj] = v;
+  if (e && s) a[idx + si - sj] = v;
+  if (e && n) a[idx + si + sj] = v;
+}
+__device__ __forceinline__ void store_mirrored(double* __restrict__ a, size_t idx, double v, int j, int i, int ny, int nx, size_t sj, size_t si, bool mirror) {
+  store_mirrored_t<double>(a, idx, v, j, i, ny, nx, sj, si, mirror);
+}
+
+// first column of row i in the set: red-black parity, fixed (four-colour), or the single column j = w - 2 i of the
+// Gauss-Seidel wavefront w = jfix (jrule 2)
+__device__ __forceinline__ int colour_jstart(const ColourSet& cs, int i) {
+  return cs.jrule == 0 ? 1 + ((i + cs.rb) & 1) : (cs.jrule == 1 ? cs.jfix : cs.jfix - 2 * i);
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
+  unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_release_gpu_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t;
+}
+
+}  // namespace mgb

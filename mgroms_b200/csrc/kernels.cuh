@@ -6,7 +6,10 @@
 namespace mgb {
 
 extern long long g_launches;   // number of kernel launches issued by this library
-void kernels_init();           // one-time function attributes (dynamic shared memory limits)
+void kernels_init();           // one-time function attributes (dynamic shared memory limits), occupancy-derived grid caps
+void note_launch_error(cudaError_t e);   // remembers the first failing launch ...
+cudaError_t take_launch_error();         // ... for the next API boundary (solver.cu: finish)
+int device_sm_count();                   // SMs of the current device (grid caps are derived from it, not hard-coded)
 
 // ---- halo (single-GPU part: physical edges; src/mg_mpi_exchange.f90) ---------------------------------
 // nh = 1 array a(nzl, 0:ny+1, 0:nx+1): homogeneous-Neumann mirror on edges without neighbour, physical corners.
@@ -29,6 +32,8 @@ struct P2PBox {
   unsigned long long* seq;            // exchanges completed at this level (local)
   unsigned int* done;                 // blocks that have read *seq; the last one advances it (local)
   int* err;                           // mapped host word: set to 1 when a poll times out
+  int* abort_flag;                    // device word raised with it: later waits return at once instead of timing out again
+  unsigned timeout_ms;                // wall-clock limit of one wait
   int nzmax;                          // slot sizing: rows are nzmax*nx, columns nzmax*ny, corners nzmax words
 };
 void launch_halo1_p2p(cudaStream_t st, double* a, int nzl, int ny, int nx, Halo1Flags f, const P2PBox& B, double* x1);
@@ -56,6 +61,13 @@ void launch_relax_B(cudaStream_t st, const LevelView& L, const ColourSet& cs);
 void launch_relax_C(cudaStream_t st, const LevelView& L, const ColourSet& cs);
 // B and C fused, for neighbour-free levels with a chunked recurrence; reads the k=1 plane x1old, writes x1new completely
 void launch_relax_BC(cudaStream_t st, const LevelView& L, const ColourSet& cs, const double* x1old, double* x1new);
+// one colour of the rank-1 red-black sweep in ONE persistent launch (A + B + C fused, kernels_relax.cu); big levels only.
+// mirror = 1 on a level without neighbour ranks (the kernel writes the Neumann halo of p and of the k=1 plane itself).
+// x1old is read, x1new is written on the whole interior (the halo exchange completes its ring when there are neighbours).
+bool relax_fused_supported(const LevelView& L);
+size_t relax_fused_num_tiles(int nx, int ny, int nz);     // flags to allocate for the level (0: never fused)
+void relax_fused_init();                                  // occupancy query / shared-memory attributes (outside any capture)
+void launch_relax_fused(cudaStream_t st, const LevelView& L, int rb, int mirror, const double* x1old, double* x1new);
 // whole relax(lev, nsweeps) of a small, neighbour-free level in one single-CTA launch (red-black only)
 bool relax_small_supported(const LevelView& L);
 void launch_relax_small(cudaStream_t st, const LevelView& L, int nsweeps, int rank1);

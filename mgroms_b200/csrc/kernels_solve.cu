@@ -3,6 +3,7 @@
 // All 3-D fields are (k,j,i) with k fastest and a one-cell halo in j and i.
 // Compiled with -fmad=false so that every expression rounds exactly like the CPU oracle's.
 #include "kernels.cuh"
+#include "device_utils.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -10,19 +11,9 @@
 namespace mgb {
 
 long long g_launches = 0;
-
-#define IDX3(k, j, i, nzl, ny2) ((size_t)(k) + (size_t)(nzl) * ((size_t)(j) + (size_t)(ny2) * (size_t)(i)))
-
-static inline unsigned blocks_for(size_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
-
-// one launch path for every kernel of this file (counts the launches for mgb_launch_count)
-template <typename... KArgs, typename... Args>
-static void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
-  ++g_launches;
-}
+static cudaError_t g_launch_err = cudaSuccess;
+void note_launch_error(cudaError_t e) { if (e != cudaSuccess && g_launch_err == cudaSuccess) g_launch_err = e; }
+cudaError_t take_launch_error() { const cudaError_t e = g_launch_err; g_launch_err = cudaSuccess; return e; }
 
 // =====================================================================================================
 // generic helpers
@@ -41,7 +32,7 @@ __global__ void k_axpy_all(double* __restrict__ y, const double* __restrict__ x,
 }
 static unsigned capped_blocks(size_t n, unsigned threads) {
   size_t b = (n + threads - 1) / threads;
-  const size_t cap = 148 * 16;
+  const size_t cap = (size_t)device_sm_count() * 16;
   return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 void launch_fill(cudaStream_t st, double* a, double v, size_t n) { if (!n) return; launch_k(k_fill, capped_blocks(n, 256), 256, 0, st, a, v, n); }
@@ -193,13 +184,25 @@ __device__ __forceinline__ void ll_store(uint4* dst, double v, unsigned tag) {
   const unsigned long long u = (unsigned long long)__double_as_longlong(v);
   asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "r"((unsigned)u), "r"(tag), "r"((unsigned)(u >> 32)), "r"(tag) : "memory");
 }
-__device__ __forceinline__ double ll_wait(const uint4* src, unsigned tag, int* err) {
-  unsigned lo, t0, hi, t1; int spins = 0;
+// Poll a mailbox word until both tags carry the number of this exchange.  A neighbour that never writes must not hang the
+// GPU: after B.timeout_ms of wall clock (globaltimer) the wait gives up, raises the mapped host word (the API call fails at
+// its end) and the device-side abort flag (every later wait of this and of the following launches returns at once).
+// `ok` turns false: the caller leaves the halo untouched instead of storing the stale word.
+__device__ __forceinline__ double ll_wait(const uint4* src, unsigned tag, const P2PBox& B, bool& ok) {
+  unsigned lo, t0, hi, t1;
+  unsigned long long start = 0; int spins = 0;
   for (;;) {
     asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo), "=r"(t0), "=r"(hi), "=r"(t1) : "l"(src) : "memory");
     if (t0 == tag && t1 == tag) break;
-    if (++spins > (1 << 23)) { *err = 1; break; }          // several seconds: a lost neighbour must not hang the GPU
-    __nanosleep(64);
+    if (!ok) break;
+    if (++spins == 64) { start = globaltimer_ns(); if (*(volatile int*)B.abort_flag) { ok = false; break; } }
+    if (spins > 64) {
+      __nanosleep(64);
+      if ((spins & 1023) == 0) {
+        if (*(volatile int*)B.abort_flag) { ok = false; break; }
+        if (globaltimer_ns() - start > (unsigned long long)B.timeout_ms * 1000000ull) { *B.err = 1; *(volatile int*)B.abort_flag = 1; ok = false; break; }
+      }
+    }
   }
   return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
 }
@@ -250,19 +253,20 @@ __global__ void __launch_bounds__(256) k_halo1_p2p(double* __restrict__ a, int n
   }
   // (2) poll my mailbox for the words of exchange s and unpack them
   const uint4* __restrict__ M = B.mine + par;
+  bool ok = true;                                          // false after a timed-out wait: nothing more is stored
   for (size_t e = tid0; e < n1; e += nthr) {
     if (e < 2 * n_ew) {
       const int side = (int)(e / n_ew); const size_t rem = e % n_ew;
-      if (side == 0 && f.west) { const double v = ll_wait(M + offW + rem, tag, B.err); a[IDX3(0, 1, 0, nzl, ny2) + rem] = v; if (x1 && rem % nzl == 0) x1[(size_t)(1 + rem / nzl)] = v; }
-      if (side == 1 && f.east) { const double v = ll_wait(M + offE + rem, tag, B.err); a[IDX3(0, 1, nx + 1, nzl, ny2) + rem] = v; if (x1 && rem % nzl == 0) x1[(size_t)(1 + rem / nzl) + (size_t)ny2 * (nx + 1)] = v; }
+      if (side == 0 && f.west) { const double v = ll_wait(M + offW + rem, tag, B, ok); if (ok) { a[IDX3(0, 1, 0, nzl, ny2) + rem] = v; if (x1 && rem % nzl == 0) x1[(size_t)(1 + rem / nzl)] = v; } }
+      if (side == 1 && f.east) { const double v = ll_wait(M + offE + rem, tag, B, ok); if (ok) { a[IDX3(0, 1, nx + 1, nzl, ny2) + rem] = v; if (x1 && rem % nzl == 0) x1[(size_t)(1 + rem / nzl) + (size_t)ny2 * (nx + 1)] = v; } }
       continue;
     }
     size_t e2 = e - 2 * n_ew;
     if (e2 < 2 * n_sn) {
       const int side = (int)(e2 / n_sn); const size_t rem = e2 % n_sn;
       const int i = 1 + (int)(rem / nzl), k = (int)(rem % nzl);
-      if (side == 0 && f.south) { const double v = ll_wait(M + offS + rem, tag, B.err); a[IDX3(k, 0, i, nzl, ny2)] = v; if (x1 && k == 0) x1[(size_t)ny2 * i] = v; }
-      if (side == 1 && f.north) { const double v = ll_wait(M + offN + rem, tag, B.err); a[IDX3(k, ny + 1, i, nzl, ny2)] = v; if (x1 && k == 0) x1[(size_t)(ny + 1) + (size_t)ny2 * i] = v; }
+      if (side == 0 && f.south) { const double v = ll_wait(M + offS + rem, tag, B, ok); if (ok) { a[IDX3(k, 0, i, nzl, ny2)] = v; if (x1 && k == 0) x1[(size_t)ny2 * i] = v; } }
+      if (side == 1 && f.north) { const double v = ll_wait(M + offN + rem, tag, B, ok); if (ok) { a[IDX3(k, ny + 1, i, nzl, ny2)] = v; if (x1 && k == 0) x1[(size_t)(ny + 1) + (size_t)ny2 * i] = v; } }
       continue;
     }
     e2 -= 2 * n_sn;
@@ -275,10 +279,11 @@ __global__ void __launch_bounds__(256) k_halo1_p2p(double* __restrict__ a, int n
     const size_t rowend = (size_t)k + (size_t)nzl * ((c == 1 || c == 2) ? nx - 1 : 0);   // i = nx or i = 1 of a received row
     const size_t colend = (size_t)k + (size_t)nzl * ((c < 2) ? 0 : ny - 1);              // j = 1 or j = ny of a received column
     double v;
-    if (diag) v = ll_wait(M + offC + (size_t)c * B.nzmax + k, tag, B.err);
-    else if (sn) v = ll_wait(M + ((c < 2) ? offS : offN) + rowend, tag, B.err);
-    else if (ew) v = ll_wait(M + ((c == 1 || c == 2) ? offE : offW) + colend, tag, B.err);
+    if (diag) v = ll_wait(M + offC + (size_t)c * B.nzmax + k, tag, B, ok);
+    else if (sn) v = ll_wait(M + ((c < 2) ? offS : offN) + rowend, tag, B, ok);
+    else if (ew) v = ll_wait(M + ((c == 1 || c == 2) ? offE : offW) + colend, tag, B, ok);
     else continue;
+    if (!ok) continue;
     a[IDX3(k, jh, ih, nzl, ny2)] = v;
     if (x1 && k == 0) x1[(size_t)jh + (size_t)ny2 * ih] = v;
   }
@@ -288,7 +293,12 @@ __global__ void __launch_bounds__(256) k_halo1_p2p(double* __restrict__ a, int n
 }
 void launch_halo1_p2p(cudaStream_t st, double* a, int nzl, int ny, int nx, Halo1Flags f, const P2PBox& B, double* x1) {
   const size_t n = (size_t)2 * ny * nzl + (size_t)2 * nx * nzl + (size_t)4 * nzl;
-  unsigned nb = blocks_for(n, 256); if (nb > 592u) nb = 592u;      // 4 blocks per SM: all co-resident (the kernel spins on its peers)
+  static const unsigned cap = []() {                                 // all blocks must be co-resident (the kernel spins on its peers)
+    int per = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_halo1_p2p, 256, 0);
+    if (per > 4) per = 4;
+    return (unsigned)(per > 0 ? per : 1) * (unsigned)device_sm_count();
+  }();
+  unsigned nb = blocks_for(n, 256); if (nb > cap) nb = cap;
   launch_k(k_halo1_p2p, nb, 256, 0, st, a, nzl, ny, nx, f, B, x1);
 }
 void launch_halo1_pre(cudaStream_t st, double* a, int nzl, int ny, int nx, Halo1Flags f, double* packS, double* packN) {
@@ -386,23 +396,6 @@ void launch_unpack_rows(cudaStream_t st, double* a, const double* buf, int nzl, 
 // =====================================================================================================
 // relaxation
 // =====================================================================================================
-// Store a freshly relaxed value and, on a level without lateral neighbour ranks, its homogeneous-Neumann mirror(s):
-// the halo cell next to an edge column (and the corner next to a corner column) takes the same value, which is what
-// fill_halo would copy afterwards (src/mg_mpi_exchange.f90:504-598).  Saves the separate halo launch per colour.
-__device__ __forceinline__ void store_mirrored(double* __restrict__ a, size_t idx, double v, int j, int i, int ny, int nx, size_t sj, size_t si, bool mirror) {
-  a[idx] = v;
-  if (!mirror) return;
-  const bool w = (i == 1), e = (i == nx), s = (j == 1), n = (j == ny);
-  if (w) a[idx - si] = v;
-  if (e) a[idx + si] = v;
-  if (s) a[idx - sj] = v;
-  if (n) a[idx + sj] = v;
-  if (w && s) a[idx - si - sj] = v;
-  if (w && n) a[idx - si + sj] = v;
-  if (e && s) a[idx + si - sj] = v;
-  if (e && n) a[idx + si + sj] = v;
-}
-
 // x1(j,i) = p(1,j,i) for every column incl. halo: snapshot of the bottom plane taken before a colour is updated
 __global__ void k_snapshot_x1(const double* __restrict__ p, double* __restrict__ x1, int nz, size_t ncols) {
   size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -411,12 +404,6 @@ __global__ void k_snapshot_x1(const double* __restrict__ p, double* __restrict__
 void launch_snapshot_x1(cudaStream_t st, const LevelView& L) {
   size_t ncols = (size_t)(L.ny + 2) * (L.nx + 2);
   launch_k(k_snapshot_x1, blocks_for(ncols, 256), 256, 0, st, L.p, L.x1, L.nz, ncols);
-}
-
-// first column of row i in the set: red-black parity, fixed (four-colour), or the single column j = w - 2 i of the
-// Gauss-Seidel wavefront w = jfix (jrule 2)
-__device__ __forceinline__ int colour_jstart(const ColourSet& cs, int i) {
-  return cs.jrule == 0 ? 1 + ((i + cs.rb) & 1) : (cs.jrule == 1 ? cs.jfix : cs.jfix - 2 * i);
 }
 
 static void relax_tiling(const LevelView& L, const ColourSet& cs, int& TI, int& TJ, int& nti, int& ntj, size_t& smem) {
@@ -438,8 +425,6 @@ static void relax_tiling(const LevelView& L, const ColourSet& cs, int& TI, int& 
 // write-back of the tile solved two steps earlier, warp 7 ("solver") only runs Thomas (one lane per column).  Named
 // barriers (bar.sync / bar.arrive) hand the buffers over, so producers never idle behind the serial Thomas phase and
 // the memory pipe is fed continuously.  Same arithmetic, operation by operation, as k_relax_A.
-__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 // NZC > 0: nz known at compile time (power of two) so that every k/j offset of the 27 operand addresses is an immediate
 // and e -> (k, column) is a shift; 0: generic.  tj_shift >= 0 when TJ is a power of two.  All element indices are 32-bit
@@ -599,7 +584,7 @@ void launch_relax_A(cudaStream_t st, const LevelView& L, const ColourSet& cs) {
   relax_tiling(L, cs, TI, TJ, nti, ntj, smem1);
   const int ntiles = nti * ntj;
   static const int minb = []() { const char* e = std::getenv("MGB_A4_CTAS"); const int v = e ? std::atoi(e) : 3; return v < 2 ? 2 : (v > 3 ? 3 : v); }();
-  const int cap = 148 * minb;
+  const int cap = device_sm_count() * minb;
   const int grid = ntiles < cap ? ntiles : cap;        // persistent: minb CTAs per SM
   int tj_shift = -1; for (int q = 0; q < 12; ++q) if ((1 << q) == TJ) tj_shift = q;
   if (minb == 2) launch_A4_nz<2>(st, L, cs, grid, 2 * smem1, TI, TJ, ntj, ntiles, tj_shift);
@@ -974,9 +959,6 @@ __global__ void __launch_bounds__(1024) k_relax_small(LevelView L, int nsweeps, 
 // Values written by other CTAs during the launch (p, q1, s, x1) are always read with ld.global.cg (L2): the L1s are not
 // coherent inside a launch.  Coefficients are read-only and stay L1-resident across sweeps (a CTA keeps its columns).
 //   bar[0]: barrier counter, bar[1]: exit counter (the last CTA to leave zeroes both for the next launch)
-__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
-  unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
-}
 template <int NZ>
 __global__ void __launch_bounds__(512, 1) k_relax_mid(LevelView L, int nsweeps, int rank1, int TC, unsigned* __restrict__ bar) {
   extern __shared__ __align__(16) double sm[];
@@ -1118,7 +1100,8 @@ bool relax_mid_supported(const LevelView& L) {
 void launch_relax_mid(cudaStream_t st, const LevelView& L, int nsweeps, int rank1, unsigned* bar) {
   const int TC = mid_tc(L);
   const int ncol = L.nx * (L.ny / 2), ntiles = (ncol + TC - 1) / TC;
-  const int G = ntiles < 148 ? ntiles : 148;
+  const int sms = device_sm_count();                                 // one CTA per SM (512 threads, launch bound 1): co-resident by construction,
+  const int G = ntiles < sms ? ntiles : sms;                         // and the cooperative launch itself refuses a grid that is not
   const int nyc = L.ny / 2, TJ = nyc < 8 ? nyc : 8;
   const size_t bc_pitch = (size_t)2 * TJ + 2 * (L.rb_chunk + L.rb_W) + 4;
   const size_t bc_doubles = 2 * bc_pitch + (size_t)L.rb_chunk * 2 * TJ + (size_t)(L.rb_chunk + L.rb_W) * (4 * bc_pitch + 2);
@@ -1129,15 +1112,20 @@ void launch_relax_mid(cudaStream_t st, const LevelView& L, int nsweeps, int rank
   cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;   // co-residency is required (grid barriers)
   cfg.attrs = at; cfg.numAttrs = 1;
   switch (L.nz) {
-    case 2: cudaLaunchKernelEx(&cfg, k_relax_mid<2>, L, nsweeps, rank1, TC, bar); break;
-    case 4: cudaLaunchKernelEx(&cfg, k_relax_mid<4>, L, nsweeps, rank1, TC, bar); break;
-    case 8: cudaLaunchKernelEx(&cfg, k_relax_mid<8>, L, nsweeps, rank1, TC, bar); break;
-    case 16: cudaLaunchKernelEx(&cfg, k_relax_mid<16>, L, nsweeps, rank1, TC, bar); break;
-    default: cudaLaunchKernelEx(&cfg, k_relax_mid<32>, L, nsweeps, rank1, TC, bar); break;
+    case 2: note_launch_error(cudaLaunchKernelEx(&cfg, k_relax_mid<2>, L, nsweeps, rank1, TC, bar)); break;
+    case 4: note_launch_error(cudaLaunchKernelEx(&cfg, k_relax_mid<4>, L, nsweeps, rank1, TC, bar)); break;
+    case 8: note_launch_error(cudaLaunchKernelEx(&cfg, k_relax_mid<8>, L, nsweeps, rank1, TC, bar)); break;
+    case 16: note_launch_error(cudaLaunchKernelEx(&cfg, k_relax_mid<16>, L, nsweeps, rank1, TC, bar)); break;
+    default: note_launch_error(cudaLaunchKernelEx(&cfg, k_relax_mid<32>, L, nsweeps, rank1, TC, bar)); break;
   }
   ++g_launches;
 }
+int device_sm_count() {
+  static const int n = []() { int dev = 0, v = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); return v > 0 ? v : 148; }();
+  return n;
+}
 void kernels_init() {
+  relax_fused_init();
   a4_attrs<2>(); a4_attrs<3>();
   cudaFuncSetAttribute(k_relax_BC, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_relax_mid<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

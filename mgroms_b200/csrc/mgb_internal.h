@@ -45,6 +45,11 @@ struct LevelView {
   double *g1, *q1, *x1, *s;   // 2-D work planes of the rank-1 correction
   double *x1b;                // second k=1 plane (double buffer of the fused B+C kernel)
   int rb_chunk, rb_W;         // the bottom recurrence runs in independent chunks of rb_chunk columns warmed up over rb_W columns
+  // fused relaxation kernel (kernels_relax.cu): per-tile "q1 published" flags stamped with the launch number, the launch
+  // counter {epoch, exit count}, the mapped host error word + device abort flag raised by a wait that times out, and that timeout
+  unsigned *tflags, *tctl;
+  int *err, *abort_flag;
+  unsigned timeout_ms;
 };
 // warm-up length of the chunked bottom recurrence: smallest w with rho^w <= 1e-20 (rho = contraction factor)
 inline int rb_warmup(double rho) { int w = 0; double acc = 1.0; while (acc > 1e-20 && w < 64) { acc *= rho; ++w; } return w; }

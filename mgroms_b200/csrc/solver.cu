@@ -86,18 +86,20 @@ struct Solver {
   Params P;
   int rank = 0, npx = 1, npy = 1, nranks = 1, device = 0;
   std::vector<Level> L;              // L[lev-1]
-  cudaStream_t st = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t st = nullptr, st_copy = nullptr;      // solver stream; PCIe copies of nhydro_solve
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_c[4] = {nullptr, nullptr, nullptr, nullptr};
   ncclComm_t comm = nullptr;
   // halo exchange over NVLink peer memory (CUDA IPC): one mailbox allocation per rank, mapped by its neighbours
   bool p2p = false;
   void* mbox = nullptr;                       // my mailbox (all levels)
   std::vector<void*> peer_mbox;               // per rank: its mailbox mapped into this process (nullptr: self / not a neighbour)
   unsigned long long* p2p_seq = nullptr; unsigned int* p2p_done = nullptr;   // per-level counters (local)
-  int* p2p_err_host = nullptr; int* p2p_err_dev = nullptr;                     // mapped host word raised by a timed-out wait
+  int* err_host = nullptr; int* err_dev = nullptr;                             // mapped host word raised by a timed-out device-side wait (1: halo exchange, 2: fused relax)
+  int* abort_dev = nullptr;                                                    // device word raised with it: later waits give up at once
+  unsigned spin_timeout_ms = 5000;                                             // MGB_SPIN_TIMEOUT_MS
   double hlim = 0, theta_b = 0, theta_s = 0;
   // level-1 model arrays (k fastest) and staging for the (i,j,k) host layout
-  double *ut = nullptr, *vt = nullptr, *wt = nullptr, *stage = nullptr, *flux = nullptr, *rmask = nullptr;
+  double *ut = nullptr, *vt = nullptr, *wt = nullptr, *stage = nullptr, *stage_v = nullptr, *stage_w = nullptr, *flux = nullptr, *rmask = nullptr;
   double *sums = nullptr;            // device scalars: [0] residual sum, [1] bnorm sum, [2] all-reduced
   int* flag_dev = nullptr;
   std::vector<void*> allocs;
@@ -108,6 +110,7 @@ struct Solver {
   bool use_mid = true;               // fused cooperative relaxation (grid barriers) on mid-size neighbour-free levels
   bool use_graph = true;             // replay one captured F-cycle (+ residual) per outer iteration
   bool fuse_halo = true;             // neighbour-free levels: relax kernels write the Neumann halo themselves
+  bool use_fused = true;             // big levels: one persistent launch per colour (A + B + C fused)
   bool fuse_bc = true;               // neighbour-free levels: kernels B and C fused
   size_t fuse_bc_limit = 3000000;    // ... up to this many points (larger levels stream better with the separate C)
   cudaGraphExec_t cycle_graph = nullptr;
@@ -179,8 +182,24 @@ static Halo1Flags flags_of(const LevelDims& d) {
 static int finish() {
   cudaError_t e = cudaStreamSynchronize(S.st);
   if (e == cudaSuccess) e = cudaGetLastError();
-  if (e != cudaSuccess) return fail(std::string("CUDA failure: ") + cudaGetErrorString(e));
-  if (S.p2p_err_host && *S.p2p_err_host) { *S.p2p_err_host = 0; return fail("halo exchange timed out waiting for a neighbour GPU (peer-memory mailbox flag never raised)"); }
+  if (e != cudaSuccess) { take_launch_error(); return fail(std::string("CUDA failure: ") + cudaGetErrorString(e)); }
+  if (e == cudaSuccess) e = take_launch_error();
+  if (e != cudaSuccess) return fail(std::string("CUDA launch failure: ") + cudaGetErrorString(e));
+  if (S.err_host && *S.err_host) {
+    const int code = *S.err_host; *S.err_host = 0;
+    if (S.abort_dev) cudaMemsetAsync(S.abort_dev, 0, sizeof(int), S.st);
+    return fail(code == 1 ? "halo exchange timed out waiting for a neighbour GPU (peer-memory mailbox flag never raised; MGB_SPIN_TIMEOUT_MS)"
+                          : "fused relaxation kernel timed out waiting for a tile flag (MGB_SPIN_TIMEOUT_MS)");
+  }
+  return 0;
+}
+
+// Ranks may enter an API call seconds apart (per-rank I/O of the host model).  The peer-memory exchange spins with a
+// timeout, MPI_Irecv/Waitany of the reference simply waits: absorb the skew with a blocking 1-element all-reduce on the
+// stream before the first mailbox exchange of the call.
+static int rank_sync() {
+  if (!S.p2p || !S.comm) return 0;
+  NC(g_nccl.AllReduce(S.sums + 4, S.sums + 5, 1, ncclDouble, ncclSum, S.comm, S.st));
   return 0;
 }
 
@@ -257,6 +276,7 @@ static int fill_halo(int lev, double* a, int nzl, int nh, double* x1 = nullptr) 
     if (any1) return fill_halo1_multi(g, a, nzl, x1);
   }
   if (nh == 1) launch_halo1_phys(S.st, a, nzl, g.d.ny, g.d.nx, g.hf); else launch_halo2_phys(S.st, a, nzl, g.d.ny, g.d.nx, g.hf);
+  if (nh == 1 && x1) launch_halo1_phys(S.st, x1, 1, g.d.ny, g.d.nx, g.hf);   // the k=1 plane mirrors like the field itself (its interior is kept by kernel C)
   bool any = false; for (int q = 0; q < 8; ++q) any |= g.d.neighb[q] >= 0;
   if (any) {
     if (!S.comm) return fail("multi-rank level but mgb_comm_init has not been called");
@@ -294,6 +314,25 @@ static int gather(int lev, const double* x, double* y, int nzl) {
 // ------------------------------------------------------------------------------------------------------
 // operators
 // ------------------------------------------------------------------------------------------------------
+// which kernels relax(lev, .) runs for the red-black smoother: "small" (one CTA), "mid" (cooperative), "fused" (one persistent
+// launch per colour), "a+bc" / "a+b+c" (separate launches), "a" (no k=1 diagonal coupling), with "+halo" when the halo is a separate launch
+static std::string relax_path(int lev) {
+  Level& g = S.L[lev - 1];
+  const std::string& m = S.P.relax_method;
+  if (!(m == "Red-Black" || m == "RB")) return m;
+  bool lonely = true; for (int q = 0; q < 8; ++q) lonely &= g.d.neighb[q] < 0;
+  const bool rank1 = (S.P.cmatrix == "real") && g.bottom_diag;
+  if (S.use_small && lonely && relax_small_supported(g.v)) return "small";
+  if (S.use_mid && lonely && relax_mid_supported(g.v)) return "mid";
+  const int fuse = (lonely && S.fuse_halo) ? 1 : 0;
+  std::string r;
+  if (!rank1) r = "a";
+  else if (S.use_fused && relax_fused_supported(g.v)) r = "fused";
+  else if (fuse && S.fuse_bc && g.v.rb_chunk < g.d.nx && g.n3() <= S.fuse_bc_limit) r = "a+bc";
+  else r = "a+b+c";
+  return fuse ? r : r + (lonely ? "+halo" : "+exchange");
+}
+
 static int relax(int lev, int nsweeps) {
   Level& g = S.L[lev - 1];
   const std::string& m = S.P.relax_method;
@@ -316,6 +355,15 @@ static int relax(int lev, int nsweeps) {
     const int xmode = fuse ? 1 : 2;                           // 2: neighbours -> C keeps x1's interior, the exchange its halo ring
     if (rank1) launch_snapshot_x1(S.st, g.v);                 // x1 = p(1,:,:) once per call; kept current afterwards
     LevelView v = g.v;
+    if (rank1 && S.use_fused && relax_fused_supported(g.v)) {  // A + B + C of a colour in one persistent launch (kernels_relax.cu)
+      for (int it = 0; it < nsweeps; ++it)
+        for (int rb = 1; rb <= 2; ++rb) {
+          launch_relax_fused(S.st, v, rb, fuse, v.x1, v.x1b);
+          { double* t = v.x1; v.x1 = v.x1b; v.x1b = t; }
+          if (!fuse) RC(fill_halo(lev, v.p, g.d.nz, 1, v.x1));
+        }
+      return 0;
+    }
     for (int it = 0; it < nsweeps; ++it)
       for (int rb = 1; rb <= 2; ++rb) {
         ColourSet cs{1, 1, 0, rb, 0, rank1 ? 1 : 0, rank1 ? xmode : fuse};
@@ -461,6 +509,7 @@ static int solve_p() {
   if (!S.have_matrices) return fail("mgb_matrices has not been called");
   Level& g = S.L[0];
   const double tol = S.P.solver_prec; const int maxite = S.P.solver_maxiter;
+  RC(rank_sync());
   launch_fill(S.st, g.v.p, 0.0, g.n3());
   CU(cudaEventRecord(S.ev0, S.st));
   TicGuard tg_solve("solve", 1);                              // src/mg_solvers.f90:45,82
@@ -530,6 +579,7 @@ static MatrixView matrix_view(Level& g, int lev) {
 static void drop_cycle_graph();
 static int define_matrices() {
   drop_cycle_graph();
+  RC(rank_sync());
   for (int lev = 1; lev <= S.nlevs(); ++lev) {
     Level& g = S.L[lev - 1];
     if (lev > 1) {
@@ -586,24 +636,29 @@ static size_t n_u() { const LevelDims& d = S.L[0].d; return (size_t)(d.nx + 1) *
 static size_t n_v() { const LevelDims& d = S.L[0].d; return (size_t)(d.nx + 2) * (d.ny + 1) * d.nz; }
 static size_t n_w() { const LevelDims& d = S.L[0].d; return (size_t)(d.nx + 2) * (d.ny + 2) * (d.nz + 1); }
 
+// Host (model-layout, i fastest) <-> device (k fastest).  The PCIe copies run on their own stream through one staging buffer
+// per array, so that the transposes of one array overlap the copy of the next (and, on the way back, the copy of u starts
+// while v and w are still being transposed).
 static int upload_uvw(const double* u, const double* v, const double* w) {
   const LevelDims& d = S.L[0].d;
-  CU(cudaMemcpyAsync(S.stage, u, n_u() * sizeof(double), cudaMemcpyHostToDevice, S.st));
-  launch_transpose_ijk_to_kji(S.st, S.stage, S.ut, d.nx + 1, d.ny + 2, d.nz);
-  CU(cudaMemcpyAsync(S.stage, v, n_v() * sizeof(double), cudaMemcpyHostToDevice, S.st));
-  launch_transpose_ijk_to_kji(S.st, S.stage, S.vt, d.nx + 2, d.ny + 1, d.nz);
-  CU(cudaMemcpyAsync(S.stage, w, n_w() * sizeof(double), cudaMemcpyHostToDevice, S.st));
-  launch_transpose_ijk_to_kji(S.st, S.stage, S.wt, d.nx + 2, d.ny + 2, d.nz + 1);
+  CU(cudaEventRecord(S.ev_c[3], S.st)); CU(cudaStreamWaitEvent(S.st_copy, S.ev_c[3], 0));     // staging buffers are free once earlier work is done
+  CU(cudaMemcpyAsync(S.stage_w, w, n_w() * sizeof(double), cudaMemcpyHostToDevice, S.st_copy)); CU(cudaEventRecord(S.ev_c[2], S.st_copy));
+  CU(cudaMemcpyAsync(S.stage, u, n_u() * sizeof(double), cudaMemcpyHostToDevice, S.st_copy));   CU(cudaEventRecord(S.ev_c[0], S.st_copy));
+  CU(cudaMemcpyAsync(S.stage_v, v, n_v() * sizeof(double), cudaMemcpyHostToDevice, S.st_copy)); CU(cudaEventRecord(S.ev_c[1], S.st_copy));
+  CU(cudaStreamWaitEvent(S.st, S.ev_c[2], 0)); launch_transpose_ijk_to_kji(S.st, S.stage_w, S.wt, d.nx + 2, d.ny + 2, d.nz + 1);
+  CU(cudaStreamWaitEvent(S.st, S.ev_c[0], 0)); launch_transpose_ijk_to_kji(S.st, S.stage, S.ut, d.nx + 1, d.ny + 2, d.nz);
+  CU(cudaStreamWaitEvent(S.st, S.ev_c[1], 0)); launch_transpose_ijk_to_kji(S.st, S.stage_v, S.vt, d.nx + 2, d.ny + 1, d.nz);
   return 0;
 }
 static int download_uvw(double* u, double* v, double* w) {
   const LevelDims& d = S.L[0].d;
-  launch_transpose_kji_to_ijk(S.st, S.ut, S.stage, d.nx + 1, d.ny + 2, d.nz);
-  CU(cudaMemcpyAsync(u, S.stage, n_u() * sizeof(double), cudaMemcpyDeviceToHost, S.st));
-  launch_transpose_kji_to_ijk(S.st, S.vt, S.stage, d.nx + 2, d.ny + 1, d.nz);
-  CU(cudaMemcpyAsync(v, S.stage, n_v() * sizeof(double), cudaMemcpyDeviceToHost, S.st));
-  launch_transpose_kji_to_ijk(S.st, S.wt, S.stage, d.nx + 2, d.ny + 2, d.nz + 1);
-  CU(cudaMemcpyAsync(w, S.stage, n_w() * sizeof(double), cudaMemcpyDeviceToHost, S.st));
+  launch_transpose_kji_to_ijk(S.st, S.ut, S.stage, d.nx + 1, d.ny + 2, d.nz);       CU(cudaEventRecord(S.ev_c[0], S.st));
+  launch_transpose_kji_to_ijk(S.st, S.vt, S.stage_v, d.nx + 2, d.ny + 1, d.nz);     CU(cudaEventRecord(S.ev_c[1], S.st));
+  launch_transpose_kji_to_ijk(S.st, S.wt, S.stage_w, d.nx + 2, d.ny + 2, d.nz + 1); CU(cudaEventRecord(S.ev_c[2], S.st));
+  CU(cudaStreamWaitEvent(S.st_copy, S.ev_c[0], 0)); CU(cudaMemcpyAsync(u, S.stage, n_u() * sizeof(double), cudaMemcpyDeviceToHost, S.st_copy));
+  CU(cudaStreamWaitEvent(S.st_copy, S.ev_c[1], 0)); CU(cudaMemcpyAsync(v, S.stage_v, n_v() * sizeof(double), cudaMemcpyDeviceToHost, S.st_copy));
+  CU(cudaStreamWaitEvent(S.st_copy, S.ev_c[2], 0)); CU(cudaMemcpyAsync(w, S.stage_w, n_w() * sizeof(double), cudaMemcpyDeviceToHost, S.st_copy));
+  CU(cudaStreamSynchronize(S.st_copy));
   return finish();
 }
 
@@ -668,12 +723,14 @@ static int clean() {
   tt_reset();
   drop_cycle_graph();
   for (void* p : S.peer_mbox) if (p) cudaIpcCloseMemHandle(p);
-  if (S.p2p_err_host) cudaFreeHost(S.p2p_err_host);
+  if (S.err_host) cudaFreeHost(S.err_host);
   for (void* p : S.allocs) cudaFree(p);
   S.allocs.clear();
   if (S.comm && g_nccl.CommDestroy) { g_nccl.CommDestroy(S.comm); }
   if (S.ev0) cudaEventDestroy(S.ev0);
   if (S.ev1) cudaEventDestroy(S.ev1);
+  for (cudaEvent_t e : S.ev_c) if (e) cudaEventDestroy(e);
+  if (S.st_copy) cudaStreamDestroy(S.st_copy);
   if (S.st) cudaStreamDestroy(S.st);
   S = Solver();
   return 0;
@@ -696,7 +753,13 @@ static int init(int nx, int ny, int nz, int npx, int npy, int rank, const char* 
   CU(cudaGetDevice(&S.device));
   S.rank = rank; S.npx = npx; S.npy = npy; S.nranks = npx * npy;
   CU(cudaStreamCreateWithFlags(&S.st, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&S.st_copy, cudaStreamNonBlocking));
   CU(cudaEventCreate(&S.ev0)); CU(cudaEventCreate(&S.ev1));
+  for (cudaEvent_t& e : S.ev_c) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  { const char* tm = std::getenv("MGB_SPIN_TIMEOUT_MS"); if (tm && std::atoll(tm) > 0) S.spin_timeout_ms = (unsigned)std::atoll(tm); }
+  CU(cudaHostAlloc((void**)&S.err_host, sizeof(int), cudaHostAllocMapped)); *S.err_host = 0;
+  CU(cudaHostGetDevicePointer((void**)&S.err_dev, S.err_host, 0));
+  { void* q = nullptr; CU(cudaMalloc(&q, 16)); S.allocs.push_back(q); CU(cudaMemsetAsync(q, 0, 16, S.st)); S.abort_dev = (int*)q; }
   S.L.resize(plan.size());
   for (size_t q = 0; q < plan.size(); ++q) {
     Level& g = S.L[q]; g.d = plan[q]; g.hf = flags_of(g.d);
@@ -713,6 +776,9 @@ static int init(int nx, int ny, int nz, int npx, int npy, int rank, const char* 
     RC(dalloc(&g.tab, (size_t)4 * (d.nz + 1)));
     if (lev == 1) { RC(dalloc(&g.dzw, (size_t)(d.nz + 1) * n2)); RC(dalloc(&g.zxdy, n3)); RC(dalloc(&g.zydx, n3)); }
     { double* q = nullptr; RC(dalloc(&q, 2)); g.gridbar = (unsigned*)q; }
+    { const size_t nt = relax_fused_num_tiles(d.nx, d.ny, d.nz);           // fused relaxation: tile flags + {epoch, exit counter}
+      if (nt) { double* q = nullptr; RC(dalloc(&q, (nt + 1) / 2)); g.v.tflags = (unsigned*)q; RC(dalloc(&q, 1)); g.v.tctl = (unsigned*)q; }
+      g.v.err = S.err_dev; g.v.abort_flag = S.abort_dev; g.v.timeout_ms = S.spin_timeout_ms; }
     g.npartials = residual_num_partials(g.v);
     RC(dalloc(&g.partials, (size_t)g.npartials));
     { void* pp = nullptr; CU(cudaMalloc(&pp, 8 * sizeof(double*))); S.allocs.push_back(pp); g.planes_dev = (double**)pp;
@@ -732,6 +798,7 @@ static int init(int nx, int ny, int nz, int npx, int npy, int rank, const char* 
   { const LevelDims& d = S.L[0].d;
     RC(dalloc(&S.ut, (size_t)(d.nx + 1) * (d.ny + 2) * d.nz)); RC(dalloc(&S.vt, (size_t)(d.nx + 2) * (d.ny + 1) * d.nz));
     RC(dalloc(&S.wt, (size_t)(d.nx + 2) * (d.ny + 2) * (d.nz + 1))); RC(dalloc(&S.stage, (size_t)(d.nx + 2) * (d.ny + 2) * (d.nz + 1)));
+    RC(dalloc(&S.stage_v, (size_t)(d.nx + 2) * (d.ny + 2) * (d.nz + 1))); RC(dalloc(&S.stage_w, (size_t)(d.nx + 2) * (d.ny + 2) * (d.nz + 1)));
     RC(dalloc(&S.flux, (size_t)(d.nx + 2) * (d.ny + 2) * (d.nz + 1))); RC(dalloc(&S.rmask, (size_t)(d.nx + 2) * (d.ny + 2)));
     RC(dalloc(&S.sums, 8));
     void* fp = nullptr; CU(cudaMalloc(&fp, sizeof(int))); S.allocs.push_back(fp); S.flag_dev = (int*)fp; }
@@ -743,6 +810,7 @@ static int init(int nx, int ny, int nz, int npx, int npy, int rank, const char* 
   S.use_mid = !(nm && nm[0] == '1');
   const char* nf = std::getenv("MGB_NO_FUSED_HALO");
   S.fuse_halo = !(nf && nf[0] == '1');
+  { const char* nfr = std::getenv("MGB_NO_FUSED_RELAX"); S.use_fused = !(nfr && nfr[0] == '1'); }
   const char* nb = std::getenv("MGB_NO_FUSED_BC");
   S.fuse_bc = !(nb && nb[0] == '1');
   { const char* fl = std::getenv("MGB_FUSE_BC_LIMIT"); if (fl) S.fuse_bc_limit = (size_t)std::atoll(fl); }
@@ -817,8 +885,6 @@ static int p2p_setup() {
   { void* q = nullptr; CU(cudaMalloc(&q, bytes)); S.allocs.push_back(q); S.mbox = q; CU(cudaMemsetAsync(q, 0, bytes, S.st)); }
   { void* q = nullptr; CU(cudaMalloc(&q, (size_t)nl * 16)); S.allocs.push_back(q); CU(cudaMemsetAsync(q, 0, (size_t)nl * 16, S.st));
     S.p2p_seq = (unsigned long long*)q; S.p2p_done = (unsigned int*)((char*)q + (size_t)nl * 8); }
-  CU(cudaHostAlloc((void**)&S.p2p_err_host, sizeof(int), cudaHostAllocMapped)); *S.p2p_err_host = 0;
-  CU(cudaHostGetDevicePointer((void**)&S.p2p_err_dev, S.p2p_err_host, 0));
   cudaIpcMemHandle_t mine;
   if (cudaIpcGetMemHandle(&mine, S.mbox) != cudaSuccess) { cudaGetLastError(); ok = 0; std::memset(&mine, 0, sizeof mine); }
   CU(cudaMemcpyAsync(hbuf + (size_t)64 * S.rank, &mine, 64, cudaMemcpyHostToDevice, S.st));
@@ -858,7 +924,7 @@ static int p2p_setup() {
       B.peer[c] = base ? (uint4*)(base + data_off[q]) : nullptr;
     }
     B.mine = (const uint4*)((char*)S.mbox + data_off[q]);
-    B.seq = S.p2p_seq + q; B.done = S.p2p_done + q; B.err = S.p2p_err_dev; B.nzmax = g.d.nz + 1;
+    B.seq = S.p2p_seq + q; B.done = S.p2p_done + q; B.err = S.err_dev; B.abort_flag = S.abort_dev; B.timeout_ms = S.spin_timeout_ms; B.nzmax = g.d.nz + 1;
   }
   S.p2p = true;
   return 0;
@@ -1015,17 +1081,18 @@ int mgb_write_fort100(const char* path) {
 double mgb_last_solve_ms(void) { return S.last_ms; }
 int mgb_last_solve_iters(void) { return S.last_iters; }
 
-int mgb_relax(int lev, int nsweeps) { RC(check_level(lev)); RC(relax(lev, nsweeps)); return finish(); }
+int mgb_relax(int lev, int nsweeps) { RC(check_level(lev)); RC(rank_sync()); RC(relax(lev, nsweeps)); return finish(); }
 int mgb_residual(int lev, double* res) {
-  RC(check_level(lev)); RC(residual(lev));
+  RC(check_level(lev)); RC(rank_sync()); RC(residual(lev));
   double s = 0; RC(global_sum(lev, S.sums, &s)); *res = std::sqrt(s); return 0;
 }
-int mgb_fine2coarse(int lev) { RC(check_level(lev)); if (lev >= S.nlevs()) return fail("no coarser level"); RC(fine2coarse(lev, false)); return finish(); }
-int mgb_coarse2fine(int lev) { RC(check_level(lev)); if (lev >= S.nlevs()) return fail("no coarser level"); RC(coarse2fine(lev, false)); return finish(); }
-int mgb_fcycle(void) { RC(check_level(1)); RC(fcycle()); return finish(); }
-int mgb_vcycle(int lev1) { RC(check_level(lev1)); RC(vcycle(lev1)); return finish(); }
+int mgb_fine2coarse(int lev) { RC(check_level(lev)); if (lev >= S.nlevs()) return fail("no coarser level"); RC(rank_sync()); RC(fine2coarse(lev, false)); return finish(); }
+int mgb_coarse2fine(int lev) { RC(check_level(lev)); if (lev >= S.nlevs()) return fail("no coarser level"); RC(rank_sync()); RC(coarse2fine(lev, false)); return finish(); }
+int mgb_fcycle(void) { RC(check_level(1)); RC(rank_sync()); RC(fcycle()); return finish(); }
+int mgb_vcycle(int lev1) { RC(check_level(lev1)); RC(rank_sync()); RC(vcycle(lev1)); return finish(); }
 int mgb_fill_halo(int lev, const char* name) {
   RC(check_level(lev)); FieldRef f; RC(field_ref(lev, name, f));
+  RC(rank_sync());
   if (f.is_cA) {                                               // fill_halo_4D, src/mg_mpi_exchange.f90:1245-1530
     Level& g = S.L[lev - 1];
     bool anynb = false; for (int q = 0; q < 8; ++q) anynb |= g.d.neighb[q] >= 0;
@@ -1077,17 +1144,31 @@ int mgb_set_field(int lev, const char* name, const double* in) {
     CU(cudaMemcpyAsync(&rho, S.sums + 3, sizeof(double), cudaMemcpyDeviceToHost, S.st));
     CU(cudaStreamSynchronize(S.st));
     g.rho = rho; g.v.rb_W = rb_warmup(rho); g.v.rb_chunk = (g.v.rb_W > RB_WMAX) ? g.d.nx : RB_CHUNK;
+    launch_any_nonzero2(S.st, g.v.c5b, g.v.c8b, g.n2(), S.flag_dev);   // the installed matrix may (or may no longer) couple the k=1 diagonals
+    int flag = 1;
+    CU(cudaMemcpyAsync(&flag, S.flag_dev, sizeof(int), cudaMemcpyDeviceToHost, S.st));
+    CU(cudaStreamSynchronize(S.st));
+    g.bottom_diag = flag != 0;
     return 0;
   }
   CU(cudaMemcpyAsync(f.ptr, in, f.n * sizeof(double), cudaMemcpyHostToDevice, S.st));
   CU(cudaStreamSynchronize(S.st)); return 0;
 }
 
+int mgb_relax_path(int lev, char* out, int cap) {
+  RC(check_level(lev));
+  if (!S.have_matrices) return fail("mgb_matrices has not been called");
+  const std::string r = relax_path(lev);
+  std::strncpy(out, r.c_str(), cap); if (cap > 0) out[cap - 1] = 0;
+  return 0;
+}
+int mgb_halo_transport(void) { return !S.comm ? 0 : (S.p2p ? 1 : 2); }
 long long mgb_launch_count(void) { return g_launches; }
 void mgb_reset_launch_count(void) { g_launches = 0; }
 
 int mgb_profile_halo(int lev, int reps, double* us_per_exchange) {
   RC(check_level(lev));
+  RC(rank_sync());
   Level& g = S.L[lev - 1];
   cudaEvent_t a, b; CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
   float ms = 0;
@@ -1106,6 +1187,7 @@ int mgb_profile_level1(int reps, double* out4) {
   if (!S.have_matrices) return fail("mgb_matrices has not been called");
   if (S.nlevs() < 2) return fail("need at least two levels");
   Level& g = S.L[0]; Level& c = S.L[1];
+  RC(rank_sync());
   cudaEvent_t a, b; CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
   float ms = 0;
   // relax: `reps` full red-black sweeps at level 1 through the production path; reported per colour half-sweep

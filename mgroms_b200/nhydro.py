@@ -71,6 +71,7 @@ def load(build_if_missing: bool = True):
     L.mgb_field_size.restype = C.c_longlong
     L.mgb_get_field.argtypes = [C.c_int, C.c_char_p, _dp]
     L.mgb_set_field.argtypes = [C.c_int, C.c_char_p, _dp]
+    L.mgb_relax_path.argtypes = [C.c_int, C.c_char_p, C.c_int]
     L.mgb_launch_count.restype = C.c_longlong
     L.mgb_reset_launch_count.restype = None
     L.mgb_profile_level1.argtypes = [C.c_int, _dp]
@@ -193,6 +194,17 @@ def history():
 def write_fort100(path="fort.100"): _chk(load().mgb_write_fort100(path.encode()))
 def last_solve_ms(): return load().mgb_last_solve_ms()
 def last_solve_iters(): return load().mgb_last_solve_iters()
+def relax_path(lev=1) -> str:
+    """Which kernels relax(lev, .) uses (diagnostic): small | mid | fused | a+bc | a+b+c | a, + "+halo" / "+exchange"."""
+    buf = C.create_string_buffer(64)
+    _chk(load().mgb_relax_path(lev, buf, 64))
+    return buf.value.decode()
+
+
+def halo_transport() -> str:
+    return {0: "none", 1: "p2p", 2: "nccl"}[load().mgb_halo_transport()]
+
+
 def launch_count(): return load().mgb_launch_count()
 def reset_launch_count(): load().mgb_reset_launch_count()
 

@@ -13,7 +13,38 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
+_NATIVE = False
 _dp = C.POINTER(C.c_double)
+
+
+def use_native_build(on: bool = True):
+    """CPU-baseline legs of bench.py: compile the oracle -O3 -march=native ON THE MACHINE THAT RUNS IT
+    instead of loading the portable libmgoracle.so that travels with the snapshot.  Must be called before the first lib()."""
+    global _NATIVE
+    assert _LIB is None or _NATIVE == on, "the oracle library is already loaded"
+    _NATIVE = on
+
+
+def _native_so() -> str:
+    import hashlib
+    flags = ""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.startswith("flags"):
+                    flags = ln; break
+    except OSError:
+        pass
+    src = os.path.join(_HERE, "mgoracle.cpp")
+    tag = hashlib.sha1((flags + str(os.path.getmtime(src))).encode()).hexdigest()[:12]
+    d = os.path.join(_HERE, "_native"); os.makedirs(d, exist_ok=True)
+    so = os.path.join(d, f"libmgoracle_{tag}.so")
+    if not os.path.exists(so):
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        tmp = so + f".{os.getpid()}.tmp"
+        subprocess.check_call([cxx, "-O3", "-march=native", "-std=c++17", "-fPIC", "-fopenmp", "-ffp-contract=off", "-w", "-shared", "-o", tmp, src])
+        os.replace(tmp, so)
+    return so
 
 
 def build(force: bool = False) -> str:
@@ -27,7 +58,7 @@ def build(force: bool = False) -> str:
 def lib():
     global _LIB
     if _LIB is None:
-        L = C.CDLL(build())
+        L = C.CDLL(_native_so() if _NATIVE else build())
         L.mgo_create.restype = C.c_void_p
         L.mgo_create.argtypes = [C.c_int] * 5 + [C.c_char_p]
         L.mgo_last_error.restype = C.c_char_p

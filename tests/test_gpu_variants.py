@@ -1,0 +1,47 @@
+"""Kernel-selection variants against the oracle, each in its own process (the library reads its knobs once per process):
+the fused one-launch-per-colour relaxation (kernels_relax.cu) forced onto small grids, with one and with several tiles per
+CTA and in every warp layout; and the unfused fall-back paths (separate halo launches, A/B/C launches) that the default
+configuration never takes on one GPU (MGB_NO_FUSED_HALO left the k=1 plane's halo stale)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+FUSED = dict(MGB_NO_SMALL_KERNEL="1", MGB_NO_MID_KERNEL="1", MGB_FUSED_MIN_TILES="32", MGB_EXPECT_PATH="fused")
+GRIDS = [("seamount", 64, 64, 16), ("rndtopo", 64, 128, 32), ("cuc", 128, 64, 64), ("seamount", 64, 64, 128), ("rndtopo", 76, 60, 32)]
+
+
+def run(env, *case):
+    e = dict(os.environ); e.update(env); e.setdefault("MGB_SPIN_TIMEOUT_MS", "3000")
+    r = subprocess.run([sys.executable, os.path.join(HERE, "variant_worker.py"), *map(str, case)], env=e, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "OK" in r.stdout, (env, case, r.stdout[-2000:], r.stderr[-2000:])
+    return r.stdout
+
+
+@pytest.mark.parametrize("case", GRIDS)
+@pytest.mark.parametrize("cap", ["0", "32", "40"])
+def test_fused_relax_forced_on_small_grids(case, cap):
+    run(dict(FUSED, MGB_F_GRID_CAP=cap), *case)
+
+
+@pytest.mark.parametrize("variant", ["1", "2", "3"])
+def test_fused_relax_warp_layouts(variant):
+    run(dict(FUSED, MGB_F_VARIANT=variant, MGB_F_GRID_CAP="40"), "cuc", 128, 64, 64, "solve")
+    run(dict(FUSED, MGB_F_VARIANT=variant), "seamount", 64, 64, 128)
+
+
+def test_fused_relax_full_solve():
+    run(dict(FUSED, MGB_F_GRID_CAP="40"), "rndtopo", 64, 128, 32, "solve")
+    run(dict(FUSED, MGB_NO_FUSED_HALO="1"), "seamount", 64, 64, 16, "solve")      # mirror = 0: halo and k=1 ring by separate launches
+
+
+@pytest.mark.parametrize("extra", [dict(), dict(MGB_NO_FUSED_RELAX="1"), dict(MGB_NO_FUSED_RELAX="1", MGB_NO_FUSED_BC="1")])
+def test_unfused_fallback_paths(extra):
+    env = dict(MGB_NO_FUSED_HALO="1", MGB_NO_MID_KERNEL="1", MGB_NO_SMALL_KERNEL="1", MGB_FUSED_MIN_TILES="32"); env.update(extra)
+    env["MGB_EXPECT_PATH"] = "a+b+c+halo" if extra else "fused+halo"
+    run(env, "rndtopo", 64, 128, 32, "solve")
+    run(dict(MGB_NO_FUSED_RELAX="1", MGB_NO_GRAPH="1"), "seamount", 32, 32, 32, "solve")
