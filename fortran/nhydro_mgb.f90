@@ -1,16 +1,27 @@
 !> nhydro_mgb.f90 -- drop-in replacement of the reference's `module nhydro` (src/nhydro.f90) that forwards every
 !> procedure to the B200 library libmgb.so through ISO_C_BINDING.  Same module name, same procedure names, same
 !> argument lists, so the ocean model (or src/mg_testseamount.f90 etc.) links against this file instead of
-!> src/nhydro.f90 + the mg_*.f90 solver sources.  (Not compiled in this repository: the build image has no Fortran
+!> src/nhydro.f90 + the solver sources (mg_relax, mg_intergrids, mg_define_matrix, mg_zr_zw, mg_compute_rhs,
+!> mg_correct_uvw, mg_gather, mg_solvers).  (Not compiled in this repository: the build image has no Fortran
 !> compiler; tests drive the same C entry points through ctypes with identically laid-out arrays.)
+!>
+!> Like src/nhydro.f90:3-8 it re-exports the reference's own support modules, which the stock drivers reach THROUGH
+!> `use nhydro`: `myrank`/`nprocs` (mg_mpi, src/mg_mpi.f90:7-8), `rp`/`ip` and the namelist (mg_namelist), tic/toc
+!> (mg_tictoc), `grid(:)` and the neighbour topology (mg_grids: the drivers read grid(1)%b, src/mg_testseamount.f90:201, and
+!> mg_mpi_exchange_ijk needs grid(1)%neighb), `fill_halo_2D_bmask` (mg_mpi_exchange, src/mg_testseamount.f90:101) and
+!> `write_netcdf` (mg_netcdf_out).  Those six files are compiled unchanged (INTEGRATION.md); they hold no solver arithmetic.
 module nhydro
 
   use iso_c_binding
   use mpi
+  use mg_mpi            ! myrank, nprocs, mg_mpi_init                      (src/mg_mpi.f90)
+  use mg_namelist       ! rp, ip, read_nhnamelist, netcdf_output ...        (src/mg_namelist.f90)
+  use mg_tictoc         ! tic, toc, print_tictoc                            (src/mg_tictoc.f90)
+  use mg_grids          ! grid(:), define_grids, define_neighbours          (src/mg_grids.f90)
+  use mg_mpi_exchange   ! fill_halo_2D_bmask for the drivers' rmask         (src/mg_mpi_exchange.f90)
+  use mg_netcdf_out     ! write_netcdf (or a stub of it when NetCDF is absent and netcdf_output=.false.)
 
   implicit none
-
-  integer(kind=4), parameter :: rp = 8, ip = 4
 
   interface
      integer(c_int) function mgb_init(nx, ny, nz, npx, npy, rank, namelist_path, device) bind(C, name='mgb_init')
@@ -52,7 +63,14 @@ module nhydro
      end function mgb_last_error
   end interface
 
-  integer(kind=ip) :: myrank = 0, nprocs = 1
+  interface
+     integer(c_int) function mgb_get_field(lev, name, out) bind(C, name='mgb_get_field')
+       import :: c_int, c_char, c_double
+       integer(c_int), value :: lev
+       character(kind=c_char), dimension(*) :: name
+       real(c_double), dimension(*) :: out
+     end function mgb_get_field
+  end interface
 
 contains
 
@@ -72,8 +90,10 @@ contains
     integer(kind=ip), intent(in) :: nx, ny, nz, npxg, npyg
     character(kind=c_char), dimension(128) :: id
     integer :: ierr, ngpus_per_node
-    call mpi_comm_rank(mpi_comm_world, myrank, ierr)       ! mg_mpi_init, src/mg_mpi.f90:12-36
-    call mpi_comm_size(mpi_comm_world, nprocs, ierr)
+    call mg_mpi_init()                                      ! myrank, nprocs of module mg_mpi (src/mg_mpi.f90:12-36)
+    call read_nhnamelist(vbrank=myrank)                     ! the drivers read netcdf_output etc. from the module (src/nhydro.f90:25)
+    call define_grids(npxg, npyg, nx, ny, nz)               ! host-side grid(:) for the drivers: topology + grid(1)%b mirror
+    call define_neighbours()                                ! (src/nhydro.f90:27-29); the solver state itself lives on the GPU
     ngpus_per_node = 8
     call mgb_check(mgb_init(nx, ny, nz, npxg, npyg, myrank, 'nh_namelist'//c_null_char, mod(myrank, ngpus_per_node)), 'nhydro_init')
     if (nprocs > 1) then                                   ! NCCL bootstrap over MPI: rank 0 creates the id, everybody joins
@@ -112,11 +132,14 @@ contains
     real(kind=rp), dimension(0:nx+1,1:ny+1,1:nz), target, intent(inout) :: va
     real(kind=rp), dimension(0:nx+1,0:ny+1,0:nz), target, intent(inout) :: wa
     call mgb_check(mgb_check_nondivergence(rmaska, ua, va, wa), 'nhydro_check_nondivergence')
+    ! the drivers dump grid(1)%b afterwards (src/mg_testseamount.f90:201): refresh the host mirror, same (k,j,i) layout
+    call mgb_check(mgb_get_field(1, 'b'//c_null_char, grid(1)%b), 'mgb_get_field(b)')
   end subroutine nhydro_check_nondivergence
 
   !--------------------------------------------------------------
   subroutine nhydro_clean()                                                    ! src/nhydro.f90:137
     call mgb_check(mgb_clean(), 'nhydro_clean')
+    call grids_dealloc()                                    ! src/nhydro.f90:139
   end subroutine nhydro_clean
 
 end module nhydro

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "obj")
 SO = os.path.join(HERE, "libmgb.so")
-SOURCES = ["host_plan.cpp", "kernels_solve.cu", "kernels_relax.cu", "kernels_setup.cu", "solver.cu"]
+SOURCES = ["host_plan.cpp", "kernels_solve.cu", "kernels_relax.cu", "kernels_bulk.cu", "kernels_setup.cu", "solver.cu"]
 HEADERS = ["mgb_internal.h", "kernels.cuh", "device_utils.cuh", os.path.join("..", "..", "include", "mgb.h")]
 
 
@@ -40,6 +40,8 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    if os.environ.get("MGB_BUILD_DEFS"):
+        force = True                      # experiment builds (-D...) always recompile
     if not force and not needs_build():
         return SO
     os.makedirs(OBJ, exist_ok=True)

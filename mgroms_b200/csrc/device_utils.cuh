@@ -46,6 +46,51 @@ __device__ __forceinline__ int colour_jstart(const ColourSet& cs, int i) {
   return cs.jrule == 0 ? 1 + ((i + cs.rb) & 1) : (cs.jrule == 1 ? cs.jfix : cs.jfix - 2 * i);
 }
 
+// Thomas solve of one column held in shared memory (tridiag, src/mg_relax.f90:308-334, with the reciprocal pivots `bet`
+// precomputed): x(k) in place, bu(k) = {bet(k), ud(k)} with ud(k) = cA(2,k+1) (0 at the top).  Same operations, in the same
+// order, as the plain loops
+//     x0 *= bet0 ; k = 1..nz-1: x(k) = (x(k) - ud(k-1) x(k-1)) bet(k) ; k = nz-2..0: x(k) = x(k) - (ud(k) bet(k)) x(k+1)
+// but the shared-memory operands of the NEXT four levels are loaded before the dependent chain of the current four runs:
+// under the load/store pressure of the producer warps an LDS costs 100+ cycles, and on the chain it made the solve 3-5x
+// slower than its FP64 latency bound (~55 cycles per level), which was what limited the relaxation kernels (profiles/summary_r02.md).
+// Returns x(0).
+template <int NZ>
+__device__ __forceinline__ double thomas_smem(double* __restrict__ x, const double2* __restrict__ bu) {
+  static_assert(NZ >= 2, "at least two levels");
+  const double2 c0 = bu[0];
+  double xm = x[0] * c0.x;
+  x[0] = xm;
+  double udp = c0.y;                                           // ud(k-1)
+  double r[4]; double2 c[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) if (1 + q < NZ) { r[q] = x[1 + q]; c[q] = bu[1 + q]; }
+#pragma unroll 1
+  for (int k0 = 1; k0 < NZ; k0 += 4) {
+    double rn[4]; double2 cn[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) if (k0 + 4 + q < NZ) { rn[q] = x[k0 + 4 + q]; cn[q] = bu[k0 + 4 + q]; }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) if (k0 + q < NZ) { xm = (r[q] - udp * xm) * c[q].x; x[k0 + q] = xm; udp = c[q].y; }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { r[q] = rn[q]; c[q] = cn[q]; }
+  }
+  // back substitution, descending from k = nz-2
+  double w[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) if (NZ - 2 - q >= 0) { r[q] = x[NZ - 2 - q]; const double2 t = bu[NZ - 2 - q]; w[q] = t.y * t.x; }
+#pragma unroll 1
+  for (int k0 = NZ - 2; k0 >= 0; k0 -= 4) {
+    double rn[4], wn[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) if (k0 - 4 - q >= 0) { rn[q] = x[k0 - 4 - q]; const double2 t = bu[k0 - 4 - q]; wn[q] = t.y * t.x; }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) if (k0 - q >= 0) { xm = r[q] - w[q] * xm; x[k0 - q] = xm; }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { r[q] = rn[q]; w[q] = wn[q]; }
+  }
+  return xm;
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 

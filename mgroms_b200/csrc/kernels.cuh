@@ -70,11 +70,12 @@ void relax_fused_init();                                  // occupancy query / s
 void launch_relax_fused(cudaStream_t st, const LevelView& L, int rb, int mirror, const double* x1old, double* x1new);
 // whole relax(lev, nsweeps) of a small, neighbour-free level in one single-CTA launch (red-black only)
 bool relax_small_supported(const LevelView& L);
-void launch_relax_small(cudaStream_t st, const LevelView& L, int nsweeps, int rank1);
+// hasnb = 1: the level has neighbour ranks and the halo travels over peer memory: the kernel runs the exchange itself after every colour
+void launch_relax_small(cudaStream_t st, const LevelView& L, int nsweeps, int rank1, int hasnb, const Halo1Flags& hf, const P2PBox& B);
 // whole relax(lev, nsweeps) of a mid-size, neighbour-free level in one cooperative launch with software grid barriers
 // (red-black only); `bar` = two zeroed device words owned by the level
 bool relax_mid_supported(const LevelView& L);
-void launch_relax_mid(cudaStream_t st, const LevelView& L, int nsweeps, int rank1, unsigned* bar);
+void launch_relax_mid(cudaStream_t st, const LevelView& L, int nsweeps, int rank1, unsigned* bar, int hasnb, const Halo1Flags& hf, const P2PBox& B);
 
 // ---- residual + norm (src/mg_relax.f90:337-515) ----------------------------------------------------------
 // r = b - A p on the interior; partial sums of r^2 per block into `partials`, then reduced in fixed order to *sum_out.
@@ -92,6 +93,11 @@ void launch_restrict8_fused(cudaStream_t st, const double* xf, int nzf, int nyf,
 // mode 1: pf += interp          (fused; caller refreshes halo(pf))
 // mode 2: as mode 1 on a neighbour-free fine level: the kernel writes the Neumann halo of pf itself (linear only)
 void launch_prolong(cudaStream_t st, const double* xc, int nzc, int nyc, int nxc, double* rf, double* pf, int linear, int mode);
+// pf += P xc (linear) on the interior of a big level, the fine field staged through shared memory by the bulk-copy engine
+// (kernels_bulk.cu); the caller refreshes the halo of pf
+bool prolong_bulk_supported(int nzc, int nyc, int nxc);
+void prolong_bulk_init();
+void launch_prolong_bulk(cudaStream_t st, const double* xc, int nzc, int nyc, int nxc, double* pf);
 void launch_axpy_all(cudaStream_t st, double* y, const double* x, size_t n);          // y += x
 void launch_add_halo_ring(cudaStream_t st, double* p, const double* r, int nz, int ny, int nx);  // p += r on the halo ring only
 void launch_fill(cudaStream_t st, double* a, double v, size_t n);

@@ -206,25 +206,29 @@ __device__ __forceinline__ double ll_wait(const uint4* src, unsigned tag, const 
   }
   return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
 }
-__global__ void __launch_bounds__(256) k_halo1_p2p(double* __restrict__ a, int nzl, int ny, int nx, Halo1Flags f, P2PBox B, double* __restrict__ x1) {
+// One exchange (number s) of an nh = 1 field by `nthr` cooperating threads (this one is number tid0): usable as a kernel of its own
+// (k_halo1_p2p) and from inside the fused relaxation kernels of small / mid-size levels, whose CTAs are co-resident.
+// CG: values of `a` written by other CTAs of the same launch are read with ld.global.cg (the L1s are not coherent).
+template <bool CG>
+__device__ __forceinline__ void halo1_p2p_body(double* a, int nzl, int ny, int nx, const Halo1Flags& f, const P2PBox& B, double* x1,
+                                               unsigned long long s, size_t tid0, size_t nthr) {
+  auto LD = [](const double* q) { return CG ? __ldcg(q) : *q; };
   const int ny2 = ny + 2;
   const size_t n_ew = (size_t)ny * nzl, n_sn = (size_t)nx * nzl;
   const size_t row = (size_t)B.nzmax * nx, col = (size_t)B.nzmax * ny;
   const size_t offS = 0, offE = row, offN = row + col, offW = 2 * row + col, offC = 2 * row + 2 * col;
   const size_t stride = offC + 4 * (size_t)B.nzmax;
-  const unsigned long long s = *B.seq + 1;                 // number of this exchange; *B.seq is advanced by the last block to leave
   const unsigned tag = (unsigned)s;
   const size_t par = (size_t)(s & 1ull) * stride;
-  const size_t tid0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
   const size_t n1 = 2 * n_ew + 2 * n_sn + 4 * (size_t)nzl;
   // (1) physical mirrors in place, boundary faces into the neighbours' mailboxes
   for (size_t e = tid0; e < n1; e += nthr) {
     if (e < 2 * n_ew) {
       const int side = (int)(e / n_ew); const size_t rem = e % n_ew;
-      if (side == 0) { const double v = a[IDX3(0, 1, 1, nzl, ny2) + rem];
+      if (side == 0) { const double v = LD(a + IDX3(0, 1, 1, nzl, ny2) + rem);
         if (f.west) ll_store(B.peer[3] + par + offE + rem, v, tag);
         else { a[IDX3(0, 1, 0, nzl, ny2) + rem] = v; if (x1 && rem % nzl == 0) x1[(size_t)(1 + rem / nzl)] = v; } }
-      else { const double v = a[IDX3(0, 1, nx, nzl, ny2) + rem];
+      else { const double v = LD(a + IDX3(0, 1, nx, nzl, ny2) + rem);
         if (f.east) ll_store(B.peer[1] + par + offW + rem, v, tag);
         else { a[IDX3(0, 1, nx + 1, nzl, ny2) + rem] = v; if (x1 && rem % nzl == 0) x1[(size_t)(1 + rem / nzl) + (size_t)ny2 * (nx + 1)] = v; } }
       continue;
@@ -233,10 +237,10 @@ __global__ void __launch_bounds__(256) k_halo1_p2p(double* __restrict__ a, int n
     if (e2 < 2 * n_sn) {
       const int side = (int)(e2 / n_sn); const size_t rem = e2 % n_sn;
       const int i = 1 + (int)(rem / nzl), k = (int)(rem % nzl);
-      if (side == 0) { const double v = a[IDX3(k, 1, i, nzl, ny2)];
+      if (side == 0) { const double v = LD(a + IDX3(k, 1, i, nzl, ny2));
         if (f.south) ll_store(B.peer[0] + par + offN + rem, v, tag);
         else { a[IDX3(k, 0, i, nzl, ny2)] = v; if (x1 && k == 0) x1[(size_t)ny2 * i] = v; } }
-      else { const double v = a[IDX3(k, ny, i, nzl, ny2)];
+      else { const double v = LD(a + IDX3(k, ny, i, nzl, ny2));
         if (f.north) ll_store(B.peer[2] + par + offS + rem, v, tag);
         else { a[IDX3(k, ny + 1, i, nzl, ny2)] = v; if (x1 && k == 0) x1[(size_t)(ny + 1) + (size_t)ny2 * i] = v; } }
       continue;
@@ -245,7 +249,7 @@ __global__ void __launch_bounds__(256) k_halo1_p2p(double* __restrict__ a, int n
     const int c = (int)(e2 / nzl), k = (int)(e2 % nzl);
     const int jc = (c < 2) ? 1 : ny, ic = (c == 1 || c == 2) ? nx : 1;            // interior corner cell of corner c (SW,SE,NE,NW)
     const int jh = (c < 2) ? 0 : ny + 1, ih = (c == 1 || c == 2) ? nx + 1 : 0;    // its halo corner
-    const double v = a[IDX3(k, jc, ic, nzl, ny2)];
+    const double v = LD(a + IDX3(k, jc, ic, nzl, ny2));
     const int diag = c == 0 ? f.sw : c == 1 ? f.se : c == 2 ? f.ne : f.nw;
     const int sn = (c < 2) ? f.south : f.north, ew = (c == 1 || c == 2) ? f.east : f.west;
     if (diag) ll_store(B.peer[4 + c] + par + offC + (size_t)((c + 2) & 3) * B.nzmax + k, v, tag);   // lands in the opposite corner slot
@@ -287,6 +291,10 @@ __global__ void __launch_bounds__(256) k_halo1_p2p(double* __restrict__ a, int n
     a[IDX3(k, jh, ih, nzl, ny2)] = v;
     if (x1 && k == 0) x1[(size_t)jh + (size_t)ny2 * ih] = v;
   }
+}
+__global__ void __launch_bounds__(256) k_halo1_p2p(double* __restrict__ a, int nzl, int ny, int nx, Halo1Flags f, P2PBox B, double* __restrict__ x1) {
+  const unsigned long long s = *B.seq + 1;                 // number of this exchange; *B.seq is advanced by the last block to leave
+  halo1_p2p_body<false>(a, nzl, ny, nx, f, B, x1, s, (size_t)blockIdx.x * blockDim.x + threadIdx.x, (size_t)gridDim.x * blockDim.x);
   // every block has read *B.seq by now; the last one to leave advances it for the next launch
   __syncthreads();
   if (threadIdx.x == 0 && atomicAdd(B.done, 1u) == gridDim.x - 1) { *B.done = 0; *B.seq = s; }
@@ -411,14 +419,15 @@ static void relax_tiling(const LevelView& L, const ColourSet& cs, int& TI, int& 
   const int nvi = (L.nx - cs.istart) / cs.istep + 1; // visited i
   static const int tile_pts = []() { const char* e = std::getenv("MGB_A4_TILE"); const int v = e ? std::atoi(e) : 1024; return v < 256 ? 256 : v; }();
   int tc_max = tile_pts / L.nz;                      // columns per tile: ~1024 points (two 25 KB buffers per CTA leave most of the L1)
-  if (tc_max < 16) tc_max = 16;
+  static const int tc_floor = []() { const char* e = std::getenv("MGB_A4_TCMIN"); const int v = e ? std::atoi(e) : 8; return v < 4 ? 4 : v; }();
+  if (tc_max < tc_floor) tc_max = tc_floor;          // nz = 128: 8 columns (3 CTAs / SM); 16 would need 99 KB per CTA (2 CTAs / SM)
   if (tc_max > 1024) tc_max = 1024;
   while (tc_max > 1 && (size_t)tc_max * (L.nz + 1) * 3 * sizeof(double) > 100 * 1024) tc_max /= 2;
   while (tc_max * L.nz > 256 && ((size_t)nyc * nvi + tc_max - 1) / tc_max < 296) tc_max /= 2;   // small level: more, smaller tiles
   TJ = nyc < tc_max ? nyc : tc_max;
   TI = tc_max / TJ; if (TI < 1) TI = 1; if (TI > nvi) TI = nvi;
   ntj = (nyc + TJ - 1) / TJ; nti = (nvi + TI - 1) / TI;
-  smem = (size_t)TI * TJ * (L.nz + 1) * 3 * sizeof(double);
+  smem = ((((size_t)TI * TJ * (L.nz + 1) + 1) & ~(size_t)1) + (size_t)2 * TI * TJ * (L.nz + 1)) * sizeof(double);
 }
 // Kernel A, warp-specialised persistent variant.  A CTA of 8 warps loops over tiles with two shared-memory tile
 // buffers: warps 0..6 ("producers") run phase 1 (27 loads per lane in flight, rhs/bet/ud -> smem buffer) and the coalesced
@@ -434,7 +443,8 @@ __global__ void __launch_bounds__(256, MINB) k_relax_A4(LevelView L, ColourSet c
   extern __shared__ __align__(16) double sm[];
   const int nz = NZC ? NZC : L.nz, ny2 = L.ny + 2, pitch = nz + 1;
   const int TC = TI * TJ;
-  const int bufsz = 3 * TC * pitch;
+  const int rhs_sz = (TC * pitch + 1) & ~1;                 // the pair array behind it must start on a 16-byte boundary
+  const int bufsz = rhs_sz + 2 * TC * pitch;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sj = nz; const int si = nz * ny2;
   const int nelem = TC * nz;
@@ -471,7 +481,7 @@ __global__ void __launch_bounds__(256, MINB) k_relax_A4(LevelView L, ColourSet c
     int n = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
       const int bsel = n & 1;
-      double* s_rhs = sm + bsel * bufsz; double* s_bet = s_rhs + TC * pitch; double* s_ud = s_bet + TC * pitch;
+      double* s_rhs = sm + bsel * bufsz; double2* s_bu = reinterpret_cast<double2*>(s_rhs + rhs_sz);   // {pivot, off-diagonal} pairs
       if (n >= 2) {                                         // tile n-2 sits solved in this buffer: write it back, then reuse the buffer
         named_bar_sync(3 + bsel, 256);
         writeback(s_rhs, tile - 2 * (int)gridDim.x);
@@ -524,8 +534,7 @@ __global__ void __launch_bounds__(256, MINB) k_relax_A4(LevelView L, ColourSet c
         }
         const int so = c * pitch + k;
         s_rhs[so] = acc;
-        s_bet[so] = bt;
-        s_ud[so] = hi ? udv : 0.0;
+        s_bu[so] = make_double2(bt, hi ? udv : 0.0);
       }
       __threadfence_block();
       named_bar_arrive(1 + bsel, 256);                      // buffer full
@@ -540,7 +549,7 @@ __global__ void __launch_bounds__(256, MINB) k_relax_A4(LevelView L, ColourSet c
     int n = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
       const int bsel = n & 1;
-      double* s_rhs = sm + bsel * bufsz; const double* s_bet = s_rhs + TC * pitch; const double* s_ud = s_bet + TC * pitch;
+      double* s_rhs = sm + bsel * bufsz; const double2* s_bu = reinterpret_cast<const double2*>(s_rhs + rhs_sz);
       named_bar_sync(1 + bsel, 256);                        // wait for the producers
       const int tile_j = tile % ntj, tile_i = tile / ntj;
       for (int c = lane; c < TC; c += 32) {
@@ -549,11 +558,15 @@ __global__ void __launch_bounds__(256, MINB) k_relax_A4(LevelView L, ColourSet c
         if (i > L.nx) continue;
         const int j = colour_jstart(cs, i) + 2 * (tile_j * TJ + cj);
         if (j > L.ny || j < 1) continue;
-        double* x = s_rhs + c * pitch; const double* bt = s_bet + c * pitch; const double* ud = s_ud + c * pitch;
-        double xm = x[0] * bt[0];
-        x[0] = xm;
-        for (int k = 1; k < nz; ++k) { xm = (x[k] - ud[k - 1] * xm) * bt[k]; x[k] = xm; }
-        for (int k = nz - 2; k >= 0; --k) { xm = x[k] - (ud[k] * bt[k]) * xm; x[k] = xm; }
+        double* x = s_rhs + c * pitch; const double2* bu = s_bu + c * pitch;
+        double xm;
+        if (NZC) xm = thomas_smem<NZC ? NZC : 2>(x, bu);
+        else {
+          xm = x[0] * bu[0].x;
+          x[0] = xm;
+          for (int k = 1; k < nz; ++k) { xm = (x[k] - bu[k - 1].y * xm) * bu[k].x; x[k] = xm; }
+          for (int k = nz - 2; k >= 0; --k) { xm = x[k] - (bu[k].y * bu[k].x) * xm; x[k] = xm; }
+        }
         if (cs.bottom_mode == 1) L.q1[(size_t)j + (size_t)ny2 * i] = xm;
       }
       __syncwarp();
@@ -804,8 +817,11 @@ void launch_relax_C(cudaStream_t st, const LevelView& L, const ColourSet& cs) {
 //   shared memory: six 2-D planes (x1, q1, c5b, c8b, g1, s) of (ny+2)*(nx+2) doubles + per-warp x1 rows
 // ASM (compile time, so that the staged operands are addressed with LDS/STS instead of generic loads):
 //   0: 3-D operands in global memory (L2) ; 1: p, cA2..8, bet staged in shared memory (b and g stay in L2) ; 2: b and g as well
+// NB (levels WITH neighbour ranks, peer-memory transport): after every colour the CTA runs the halo exchange itself
+// (halo1_p2p_body: stores into the neighbours' mailboxes, polls its own); the Neumann mirrors written on sides that have a
+// neighbour are overwritten by it.  `nsweeps` sweeps = 2 nsweeps exchanges, numbered from *B.seq + 1.
 template <int NZ, int ASM>
-__global__ void __launch_bounds__(1024) k_relax_small(LevelView L, int nsweeps, int rank1) {
+__global__ void __launch_bounds__(1024) k_relax_small(LevelView L, int nsweeps, int rank1, int hasnb, Halo1Flags hf, P2PBox B) {
   constexpr int all_smem = ASM;
   extern __shared__ __align__(16) double sm[];
   const int nx = L.nx, ny = L.ny, ny2 = ny + 2, nyc = ny / 2;
@@ -831,6 +847,7 @@ __global__ void __launch_bounds__(1024) k_relax_small(LevelView L, int nsweeps, 
   // x1 = p(1,:,:) once; afterwards the final stores of each colour keep it (and the Neumann halo of p) current
   if (rank1) { for (int e = threadIdx.x; e < n2; e += blockDim.x) x1[e] = p[(size_t)e * NZ]; __syncthreads(); }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const unsigned long long seq0 = hasnb ? *B.seq : 0ull; int nex = 0;
 #ifdef MGB_SMALL_TIMING
   long long tA = 0, tB = 0, tC = 0, t0 = clock64();
 #define SM_T(acc) { const long long t1 = clock64(); acc += t1 - t0; t0 = t1; }
@@ -944,7 +961,12 @@ __global__ void __launch_bounds__(1024) k_relax_small(LevelView L, int nsweeps, 
       __syncthreads();
       SM_T(tC)
     }
+    if (hasnb) {
+      halo1_p2p_body<false>(p, NZ, ny, nx, hf, B, rank1 ? x1 : nullptr, seq0 + (unsigned long long)(++nex), threadIdx.x, blockDim.x);
+      __syncthreads();
+    }
   }
+  if (hasnb && threadIdx.x == 0) *B.seq = seq0 + (unsigned long long)nex;
 #ifdef MGB_SMALL_TIMING
   if (threadIdx.x == 0 && nsweeps >= 20) printf("small nz=%d nx=%d ny=%d threads=%d W=%d all_smem=%d: per colour cycles A=%lld B=%lld C=%lld\n", NZ, nx, ny, (int)blockDim.x, L.rb_W, all_smem,
          tA / (2 * nsweeps), tB / (2 * nsweeps), tC / (2 * nsweeps));
@@ -959,15 +981,17 @@ __global__ void __launch_bounds__(1024) k_relax_small(LevelView L, int nsweeps, 
 // Values written by other CTAs during the launch (p, q1, s, x1) are always read with ld.global.cg (L2): the L1s are not
 // coherent inside a launch.  Coefficients are read-only and stay L1-resident across sweeps (a CTA keeps its columns).
 //   bar[0]: barrier counter, bar[1]: exit counter (the last CTA to leave zeroes both for the next launch)
+// NB (levels WITH neighbour ranks, peer-memory transport): every colour ends with the halo exchange run by all CTAs of the
+// launch (halo1_p2p_body) and one more grid barrier; see k_relax_small.
 template <int NZ>
-__global__ void __launch_bounds__(512, 1) k_relax_mid(LevelView L, int nsweeps, int rank1, int TC, unsigned* __restrict__ bar) {
+__global__ void __launch_bounds__(512, 1) k_relax_mid(LevelView L, int nsweeps, int rank1, int TC, unsigned* __restrict__ bar, int hasnb, Halo1Flags hf, P2PBox B) {
   extern __shared__ __align__(16) double sm[];
   const int nx = L.nx, ny = L.ny, ny2 = ny + 2, nyc = ny / 2, pitch = NZ + 1;
   constexpr int sj = NZ; const int si = NZ * ny2;
   const int G = gridDim.x;
   const int ncol = nx * nyc;                                  // columns of one colour; column c -> row i = 1 + c / nyc
   const int ntiles = (ncol + TC - 1) / TC;
-  double* s_rhs = sm; double* s_bet = sm + TC * pitch; double* s_ud = s_bet + TC * pitch;
+  double* s_rhs = sm; double2* s_bu = reinterpret_cast<double2*>(sm + TC * pitch);     // {pivot, off-diagonal} pairs
   unsigned target = 0;
   auto gbar = [&]() {
     target += G;
@@ -984,6 +1008,7 @@ __global__ void __launch_bounds__(512, 1) k_relax_mid(LevelView L, int nsweeps, 
   const double* __restrict__ c8 = L.cA[7];
   double* p = L.p;
   double* x1cur = L.x1; double* x1alt = L.x1b;
+  const unsigned long long seq0 = hasnb ? *B.seq : 0ull; int nex = 0;
   if (rank1) {   // x1 = p(1,:,:) on the whole plane incl. the halo; afterwards every colour writes the next k=1 plane completely
     const int n2 = ny2 * (nx + 2);
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n2; e += G * blockDim.x) x1cur[e] = __ldcg(p + (size_t)e * NZ);
@@ -1039,17 +1064,11 @@ __global__ void __launch_bounds__(512, 1) k_relax_mid(LevelView L, int nsweeps, 
           acc = acc - L.c8b[c2d + 1 + ny2] * __ldcg(x1cur + c2d + 1 + ny2);
         }
         const int so = cl * pitch + k;
-        s_rhs[so] = acc; s_bet[so] = bt; s_ud[so] = hi ? udv : 0.0;
+        s_rhs[so] = acc; s_bu[so] = make_double2(bt, hi ? udv : 0.0);
       }
       __syncthreads();
       for (int cl = threadIdx.x; cl < tcn; cl += blockDim.x) {
-        double* x = s_rhs + cl * pitch; const double* bt = s_bet + cl * pitch; const double* ud = s_ud + cl * pitch;
-        double xm = x[0] * bt[0];
-        x[0] = xm;
-#pragma unroll
-        for (int k = 1; k < NZ; ++k) { xm = (x[k] - ud[k - 1] * xm) * bt[k]; x[k] = xm; }
-#pragma unroll
-        for (int k = NZ - 2; k >= 0; --k) { xm = x[k] - (ud[k] * bt[k]) * xm; x[k] = xm; }
+        const double xm = thomas_smem<NZ>(s_rhs + cl * pitch, s_bu + cl * pitch);
         if (rank1) { const int c = cbase + cl; const int i = 1 + c / nyc, jc = c - (i - 1) * nyc; L.q1[1 + ((i + rb) & 1) + 2 * jc + ny2 * i] = xm; }
       }
       __syncthreads();
@@ -1080,6 +1099,11 @@ __global__ void __launch_bounds__(512, 1) k_relax_mid(LevelView L, int nsweeps, 
       gbar();
       MID_T(tB2)
     }
+    if (hasnb) {
+      halo1_p2p_body<true>(p, NZ, ny, nx, hf, B, rank1 ? x1cur : nullptr, seq0 + (unsigned long long)(++nex),
+                           (size_t)blockIdx.x * blockDim.x + threadIdx.x, (size_t)G * blockDim.x);
+      gbar();
+    }
   }
 #ifdef MGB_MID_TIMING
   if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == G - 1))
@@ -1088,7 +1112,7 @@ __global__ void __launch_bounds__(512, 1) k_relax_mid(LevelView L, int nsweeps, 
 #endif
   // leave the counters zeroed for the next launch: the last CTA out does it
   __syncthreads();
-  if (threadIdx.x == 0) { __threadfence(); if (atomicAdd(bar + 1, 1u) == (unsigned)G - 1) { bar[0] = 0; bar[1] = 0; } }
+  if (threadIdx.x == 0) { __threadfence(); if (atomicAdd(bar + 1, 1u) == (unsigned)G - 1) { bar[0] = 0; bar[1] = 0; if (hasnb) *B.seq = seq0 + (unsigned long long)nex; } }
 }
 static int mid_tc(const LevelView& L) { (void)L; return 64; }
 static size_t mid_limit() { static const size_t v = []() { const char* e = std::getenv("MGB_MID_LIMIT"); return e ? (size_t)std::atoll(e) : (size_t)1500000; }(); return v; }
@@ -1097,7 +1121,7 @@ bool relax_mid_supported(const LevelView& L) {
   const size_t n3 = (size_t)L.nz * (L.ny + 2) * (L.nx + 2);
   return nz_ok && (L.ny % 2 == 0) && n3 <= mid_limit() && L.rb_W <= RB_WMAX;   // chunked recurrence only
 }
-void launch_relax_mid(cudaStream_t st, const LevelView& L, int nsweeps, int rank1, unsigned* bar) {
+void launch_relax_mid(cudaStream_t st, const LevelView& L, int nsweeps, int rank1, unsigned* bar, int hasnb, const Halo1Flags& hf, const P2PBox& B) {
   const int TC = mid_tc(L);
   const int ncol = L.nx * (L.ny / 2), ntiles = (ncol + TC - 1) / TC;
   const int sms = device_sm_count();                                 // one CTA per SM (512 threads, launch bound 1): co-resident by construction,
@@ -1112,11 +1136,11 @@ void launch_relax_mid(cudaStream_t st, const LevelView& L, int nsweeps, int rank
   cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;   // co-residency is required (grid barriers)
   cfg.attrs = at; cfg.numAttrs = 1;
   switch (L.nz) {
-    case 2: note_launch_error(cudaLaunchKernelEx(&cfg, k_relax_mid<2>, L, nsweeps, rank1, TC, bar)); break;
-    case 4: note_launch_error(cudaLaunchKernelEx(&cfg, k_relax_mid<4>, L, nsweeps, rank1, TC, bar)); break;
-    case 8: note_launch_error(cudaLaunchKernelEx(&cfg, k_relax_mid<8>, L, nsweeps, rank1, TC, bar)); break;
-    case 16: note_launch_error(cudaLaunchKernelEx(&cfg, k_relax_mid<16>, L, nsweeps, rank1, TC, bar)); break;
-    default: note_launch_error(cudaLaunchKernelEx(&cfg, k_relax_mid<32>, L, nsweeps, rank1, TC, bar)); break;
+    case 2: note_launch_error(cudaLaunchKernelEx(&cfg, k_relax_mid<2>, L, nsweeps, rank1, TC, bar, hasnb, hf, B)); break;
+    case 4: note_launch_error(cudaLaunchKernelEx(&cfg, k_relax_mid<4>, L, nsweeps, rank1, TC, bar, hasnb, hf, B)); break;
+    case 8: note_launch_error(cudaLaunchKernelEx(&cfg, k_relax_mid<8>, L, nsweeps, rank1, TC, bar, hasnb, hf, B)); break;
+    case 16: note_launch_error(cudaLaunchKernelEx(&cfg, k_relax_mid<16>, L, nsweeps, rank1, TC, bar, hasnb, hf, B)); break;
+    default: note_launch_error(cudaLaunchKernelEx(&cfg, k_relax_mid<32>, L, nsweeps, rank1, TC, bar, hasnb, hf, B)); break;
   }
   ++g_launches;
 }
@@ -1126,6 +1150,7 @@ int device_sm_count() {
 }
 void kernels_init() {
   relax_fused_init();
+  prolong_bulk_init();
   a4_attrs<2>(); a4_attrs<3>();
   cudaFuncSetAttribute(k_relax_BC, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_relax_mid<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -1159,7 +1184,7 @@ bool relax_small_supported(const LevelView& L) {
   // larger levels go to the cooperative multi-CTA kernel (~7 us per colour floor); a single CTA beats that on 16x16 and on 2-level grids up to 32x32
   return nz_ok && (L.ny % 2 == 0) && (n2 <= (size_t)18 * 18 || (L.nz == 2 && n2 <= (size_t)34 * 34));
 }
-void launch_relax_small(cudaStream_t st, const LevelView& L, int nsweeps, int rank1) {
+void launch_relax_small(cudaStream_t st, const LevelView& L, int nsweeps, int rank1, int hasnb, const Halo1Flags& hf, const P2PBox& B) {
   const size_t n2 = (size_t)(L.ny + 2) * (L.nx + 2);
   size_t smem = (n2 * 6 + (size_t)16 * (L.ny + 2)) * sizeof(double);
   const size_t smem11 = smem + (size_t)11 * L.nz * n2 * sizeof(double), smem9 = smem + (size_t)9 * L.nz * n2 * sizeof(double);
@@ -1168,9 +1193,9 @@ void launch_relax_small(cudaStream_t st, const LevelView& L, int nsweeps, int ra
   int threads = 64; const int ncol = L.nx * (L.ny / 2);
   while (threads < ncol && threads < 1024) threads *= 2;
 #define SMALL_CASE(NZv) \
-  if (all_smem == 2) launch_k(k_relax_small<NZv, 2>, 1, threads, smem, st, L, nsweeps, rank1); \
-  else if (all_smem == 1) launch_k(k_relax_small<NZv, 1>, 1, threads, smem, st, L, nsweeps, rank1); \
-  else launch_k(k_relax_small<NZv, 0>, 1, threads, smem, st, L, nsweeps, rank1);
+  if (all_smem == 2) launch_k(k_relax_small<NZv, 2>, 1, threads, smem, st, L, nsweeps, rank1, hasnb, hf, B); \
+  else if (all_smem == 1) launch_k(k_relax_small<NZv, 1>, 1, threads, smem, st, L, nsweeps, rank1, hasnb, hf, B); \
+  else launch_k(k_relax_small<NZv, 0>, 1, threads, smem, st, L, nsweeps, rank1, hasnb, hf, B);
   switch (L.nz) {
     case 2: SMALL_CASE(2) break;
     case 4: SMALL_CASE(4) break;

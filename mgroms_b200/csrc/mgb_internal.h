@@ -45,9 +45,10 @@ struct LevelView {
   double *g1, *q1, *x1, *s;   // 2-D work planes of the rank-1 correction
   double *x1b;                // second k=1 plane (double buffer of the fused B+C kernel)
   int rb_chunk, rb_W;         // the bottom recurrence runs in independent chunks of rb_chunk columns warmed up over rb_W columns
-  // fused relaxation kernel (kernels_relax.cu): per-tile "q1 published" flags stamped with the launch number, the launch
-  // counter {epoch, exit count}, the mapped host error word + device abort flag raised by a wait that times out, and that timeout
-  unsigned *tflags, *tctl;
+  // fused relaxation kernel (kernels_relax.cu): the k=1 plane of q as tagged 16-byte words {lo, launch, hi, launch}, the launch
+  // counter {number, exit count}, the mapped host error word + device abort flag raised by a wait that times out, and that timeout
+  void* q1t;
+  unsigned* tctl;
   int *err, *abort_flag;
   unsigned timeout_ms;
 };

@@ -110,6 +110,7 @@ struct Solver {
   bool use_mid = true;               // fused cooperative relaxation (grid barriers) on mid-size neighbour-free levels
   bool use_graph = true;             // replay one captured F-cycle (+ residual) per outer iteration
   bool fuse_halo = true;             // neighbour-free levels: relax kernels write the Neumann halo themselves
+  bool fuse_exchange = true;         // small / mid levels with neighbour ranks: the relax kernel runs the peer-memory exchange itself
   bool use_fused = true;             // big levels: one persistent launch per colour (A + B + C fused)
   bool fuse_bc = true;               // neighbour-free levels: kernels B and C fused
   size_t fuse_bc_limit = 3000000;    // ... up to this many points (larger levels stream better with the separate C)
@@ -322,15 +323,18 @@ static std::string relax_path(int lev) {
   if (!(m == "Red-Black" || m == "RB")) return m;
   bool lonely = true; for (int q = 0; q < 8; ++q) lonely &= g.d.neighb[q] < 0;
   const bool rank1 = (S.P.cmatrix == "real") && g.bottom_diag;
-  if (S.use_small && lonely && relax_small_supported(g.v)) return "small";
-  if (S.use_mid && lonely && relax_mid_supported(g.v)) return "mid";
+  const bool inkernel_ok = lonely || (S.p2p && S.fuse_exchange);
+  if (S.use_small && inkernel_ok && relax_small_supported(g.v)) return lonely ? "small" : "small+p2p";
+  if (S.use_mid && inkernel_ok && relax_mid_supported(g.v)) return lonely ? "mid" : "mid+p2p";
   const int fuse = (lonely && S.fuse_halo) ? 1 : 0;
   std::string r;
   if (!rank1) r = "a";
   else if (S.use_fused && relax_fused_supported(g.v)) r = "fused";
   else if (fuse && S.fuse_bc && g.v.rb_chunk < g.d.nx && g.n3() <= S.fuse_bc_limit) r = "a+bc";
   else r = "a+b+c";
-  return fuse ? r : r + (lonely ? "+halo" : "+exchange");
+  r = fuse ? r : r + (lonely ? "+halo" : "+exchange");
+  if (rank1) r += " W=" + std::to_string(g.v.rb_W);            // warm-up rows of the chunked bottom recurrence
+  return r;
 }
 
 static int relax(int lev, int nsweeps) {
@@ -340,12 +344,15 @@ static int relax(int lev, int nsweeps) {
   const bool real_matrix = (S.P.cmatrix == "real");
   if (m == "Red-Black" || m == "RB") {
     bool lonely = true; for (int q = 0; q < 8; ++q) lonely &= g.d.neighb[q] < 0;
-    if (S.use_small && lonely && relax_small_supported(g.v)) {
-      launch_relax_small(S.st, g.v, nsweeps, (real_matrix && g.bottom_diag) ? 1 : 0);
+    // small and mid-size levels: the whole relax call in one launch; with neighbour ranks the kernel runs the peer-memory halo
+    // exchange itself after every colour (the NCCL transport keeps the separate launches)
+    const bool inkernel_ok = lonely || (S.p2p && S.fuse_exchange);
+    if (S.use_small && inkernel_ok && relax_small_supported(g.v)) {
+      launch_relax_small(S.st, g.v, nsweeps, (real_matrix && g.bottom_diag) ? 1 : 0, lonely ? 0 : 1, g.hf, g.box);
       return 0;
     }
-    if (S.use_mid && lonely && relax_mid_supported(g.v)) {
-      launch_relax_mid(S.st, g.v, nsweeps, (real_matrix && g.bottom_diag) ? 1 : 0, g.gridbar);
+    if (S.use_mid && inkernel_ok && relax_mid_supported(g.v)) {
+      launch_relax_mid(S.st, g.v, nsweeps, (real_matrix && g.bottom_diag) ? 1 : 0, g.gridbar, lonely ? 0 : 1, g.hf, g.box);
       return 0;
     }
     const bool rank1 = real_matrix && g.bottom_diag;
@@ -459,7 +466,8 @@ static int coarse2fine(int lev, bool fused) {
   if (fused) {   // p_f += P p_c on the interior, then refresh halo(p_f): identical to the reference whenever halo(p_f) was consistent
     bool lonely = true; for (int q = 0; q < 8; ++q) lonely &= f.d.neighb[q] < 0;
     if (lonely && linear && S.fuse_halo && f.n3() <= (size_t)3000000) { launch_prolong(S.st, pc, c.d.nz, nyc, nxc, f.v.r, f.v.p, linear, 2); return 0; }   // latency-bound levels: halo written by the kernel (on big levels the mirror code costs more than the launch)
-    launch_prolong(S.st, pc, c.d.nz, nyc, nxc, f.v.r, f.v.p, linear, 1);
+    if (linear && prolong_bulk_supported(c.d.nz, nyc, nxc)) launch_prolong_bulk(S.st, pc, c.d.nz, nyc, nxc, f.v.p);
+    else launch_prolong(S.st, pc, c.d.nz, nyc, nxc, f.v.r, f.v.p, linear, 1);
     RC(fill_halo(lev, f.v.p, f.d.nz, 1));
   } else {       // the reference's sequence: r_f = P p_c ; halo(r_f) ; p_f += r_f everywhere
     launch_prolong(S.st, pc, c.d.nz, nyc, nxc, f.v.r, f.v.p, linear, 0);
@@ -776,8 +784,8 @@ static int init(int nx, int ny, int nz, int npx, int npy, int rank, const char* 
     RC(dalloc(&g.tab, (size_t)4 * (d.nz + 1)));
     if (lev == 1) { RC(dalloc(&g.dzw, (size_t)(d.nz + 1) * n2)); RC(dalloc(&g.zxdy, n3)); RC(dalloc(&g.zydx, n3)); }
     { double* q = nullptr; RC(dalloc(&q, 2)); g.gridbar = (unsigned*)q; }
-    { const size_t nt = relax_fused_num_tiles(d.nx, d.ny, d.nz);           // fused relaxation: tile flags + {epoch, exit counter}
-      if (nt) { double* q = nullptr; RC(dalloc(&q, (nt + 1) / 2)); g.v.tflags = (unsigned*)q; RC(dalloc(&q, 1)); g.v.tctl = (unsigned*)q; }
+    { const size_t nt = relax_fused_num_tiles(d.nx, d.ny, d.nz);           // fused relaxation: tagged q1 plane + {launch number, exit counter}
+      if (nt) { double* q = nullptr; RC(dalloc(&q, 2 * n2)); g.v.q1t = q; RC(dalloc(&q, 1)); g.v.tctl = (unsigned*)q; }
       g.v.err = S.err_dev; g.v.abort_flag = S.abort_dev; g.v.timeout_ms = S.spin_timeout_ms; }
     g.npartials = residual_num_partials(g.v);
     RC(dalloc(&g.partials, (size_t)g.npartials));
@@ -810,6 +818,7 @@ static int init(int nx, int ny, int nz, int npx, int npy, int rank, const char* 
   S.use_mid = !(nm && nm[0] == '1');
   const char* nf = std::getenv("MGB_NO_FUSED_HALO");
   S.fuse_halo = !(nf && nf[0] == '1');
+  { const char* nfe = std::getenv("MGB_NO_FUSED_EXCHANGE"); S.fuse_exchange = !(nfe && nfe[0] == '1'); }
   { const char* nfr = std::getenv("MGB_NO_FUSED_RELAX"); S.use_fused = !(nfr && nfr[0] == '1'); }
   const char* nb = std::getenv("MGB_NO_FUSED_BC");
   S.fuse_bc = !(nb && nb[0] == '1');

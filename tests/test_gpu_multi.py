@@ -1,6 +1,10 @@
-"""Multi-GPU parity: one process per GPU (NCCL halo exchange, all-reduce, mg_gather), compared with the CPU oracle run
-with the SAME npx x npy decomposition (a 1-rank and an N-rank reference legitimately differ).
-Needs >= 2 GPUs; run with `gpurun --gpus 2|4 -- python -m pytest tests/test_gpu_multi.py -m gpu`."""
+"""Multi-GPU parity: one process per GPU (peer-memory or NCCL halo exchange, all-reduce, mg_gather), compared with the CPU
+oracle run with the SAME npx x npy decomposition (a 1-rank and an N-rank reference legitimately differ).
+Every configuration runs with both halo transports (NVLink peer-memory mailboxes, and the NCCL send/recv fallback forced by
+MGB_NO_P2P=1).  Needs >= 2 GPUs; run with `gpurun --gpus 2|4|8 -- python -m pytest tests/test_gpu_multi.py -m gpu`
+(logs of such runs: profiles/r02_gputest_multi_n*.log).  bench.py repeats two of these cases on its live communicator
+before every multi-GPU measurement (`parity` in its JSON line)."""
+import os
 import socket
 
 import numpy as np
@@ -21,14 +25,15 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world, port, cfg, out):
+def _worker(rank, world, port, cfg, env, out):
+    os.environ.update(env)            # the library reads its knobs at init / first use: this is a fresh (spawned) process
     import torch
     import torch.distributed as dist
     from mgroms_b200 import nhydro as nh
     from common import geometry, velocities
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     try:
-        kind, nx, ny, nz, npx, npy, params, uvw = cfg
+        kind, nx, ny, nz, npx, npy, params, uvw = cfg[:8]
         nh.reset_params(); nh.set_params(**params)
         nh.nhydro_init(nx, ny, nz, npx, npy, rank, device=rank)
         box = [nh.comm_unique_id() if rank == 0 else None]
@@ -40,7 +45,8 @@ def _worker(rank, world, port, cfg, out):
         nh.nhydro_matrices(dx, dy, zeta, h, rm, vert["hc"], vert["theta_b"], vert["theta_s"])
         u, v, w = velocities(uvw, nx, ny, nz, npx, npy, rank)
         nh.compute_rhs(rm, u, v, w)
-        res = {"b": nh.get_field("b"), "cA": [nh.get_field("cA", l) for l in range(1, nh.nlevs() + 1)]}
+        res = {"b": nh.get_field("b"), "cA": [nh.get_field("cA", l) for l in range(1, nh.nlevs() + 1)],
+               "transport": nh.halo_transport(), "paths": [nh.relax_path(l) for l in range(1, nh.nlevs() + 1)]}
         nh.solve_p()
         res["hist"] = nh.history()[0]; res["p"] = nh.get_field("p")
         nh.correct_uvw(u, v, w); res["u"] = u
@@ -53,11 +59,11 @@ def _worker(rank, world, port, cfg, out):
         dist.destroy_process_group()
 
 
-def run_world(cfg):
+def run_world(cfg, env):
     import torch.multiprocessing as mp
     world = cfg[4] * cfg[5]
     ctx = mp.get_context("spawn"); out = ctx.Queue(); port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, cfg, out)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, cfg, env, out)) for r in range(world)]
     for p in procs:
         p.start()
     res = dict(out.get(timeout=600) for _ in procs)
@@ -76,12 +82,27 @@ CFGS = [
     ("seamount", 16, 32, 16, 4, 2, dict(solver_prec=1e-10, solver_maxiter=20, nsmall=16), "random"),   # C4-like: two gather stages on 8 GPUs
     ("rndtopo", 16, 32, 16, 2, 1, dict(solver_prec=1e-10, solver_maxiter=30, bmask=True), "random"),     # bmask: masked walls + cA halo exchange
     ("seamount", 16, 16, 16, 2, 2, dict(solver_prec=1e-10, solver_maxiter=30, bmask=True, nsmall=16), "random"),
+    # per-rank level 1 large enough to leave the small / mid kernels (A/B/C launches + exchange with neighbours)
+    ("rndtopo", 64, 64, 32, 2, 1, dict(solver_prec=1e-10, solver_maxiter=20), "random"),
+    ("seamount", 64, 64, 32, 2, 2, dict(solver_prec=1e-10, solver_maxiter=20), "wminus1"),
+    ("rndtopo", 64, 64, 32, 4, 2, dict(solver_prec=1e-10, solver_maxiter=20, nsmall=32), "random"),
+    # the fused one-launch-per-colour relaxation on levels WITH neighbours (forced onto a small grid), k=1 ring by the exchange
+    ("cuc", 64, 128, 32, 2, 1, dict(solver_prec=1e-9, solver_maxiter=20), "wminus1", dict(MGB_FUSED_MIN_TILES="32", MGB_NO_MID_KERNEL="1", MGB_NO_SMALL_KERNEL="1"), "fused"),
+    ("seamount", 64, 64, 64, 2, 2, dict(solver_prec=1e-10, solver_maxiter=20), "random", dict(MGB_FUSED_MIN_TILES="32", MGB_F_GRID_CAP="40"), "fused"),
+    ("rndtopo", 64, 64, 32, 4, 2, dict(solver_prec=1e-10, solver_maxiter=20), "random", dict(MGB_FUSED_MIN_TILES="32"), "fused"),
 ]
 
 
-@pytest.mark.parametrize("cfg", CFGS)
-def test_multi_gpu_matches_oracle_with_same_decomposition(cfg):
-    kind, nx, ny, nz, npx, npy, params, uvw = cfg
+@pytest.mark.parametrize("transport", ["p2p", "nccl"])
+@pytest.mark.parametrize("cfg", CFGS, ids=lambda c: f"{c[0]}-{c[1]}x{c[2]}x{c[3]}-{c[4]}x{c[5]}" + ("-bmask" if c[6].get("bmask") else "") + ("-fused" if len(c) > 8 else ""))
+def test_multi_gpu_matches_oracle_with_same_decomposition(cfg, transport):
+    kind, nx, ny, nz, npx, npy, params, uvw = cfg[:8]
+    only = os.environ.get("MGB_TEST_ONLY_WORLD")        # e.g. 8 on an 8-GPU lease: skip the 2- and 4-rank configurations there
+    if only and int(only) != npx * npy:
+        pytest.skip(f"MGB_TEST_ONLY_WORLD={only}")
+    env = dict(cfg[8]) if len(cfg) > 8 else {}
+    env["MGB_NO_P2P"] = "0" if transport == "p2p" else "1"
+    env.setdefault("MGB_SPIN_TIMEOUT_MS", "5000")
     if _ngpu() < npx * npy:
         pytest.skip(f"needs {npx * npy} GPUs")
     from common import history_close, relerr
@@ -90,8 +111,12 @@ def test_multi_gpu_matches_oracle_with_same_decomposition(cfg):
     o.compute_rhs()
     b_or = [o.get("b", 1, r) for r in range(npx * npy)]
     o.solve_p(); o.correct_uvw()
-    res = run_world(cfg)
+    res = run_world(cfg, env)
     for r in range(npx * npy):
+        if transport == "nccl":
+            assert res[r]["transport"] == "nccl"
+        if len(cfg) > 9:
+            assert res[r]["paths"][0].startswith(cfg[9]), res[r]["paths"]
         for lev in range(1, o.nlevs + 1):
             assert np.array_equal(res[r]["cA"][lev - 1], o.get("cA", lev, r)), (r, lev)
         assert np.array_equal(res[r]["b"][1:-1, 1:-1], b_or[r][1:-1, 1:-1]), r

@@ -134,8 +134,9 @@ def test_seamount64_history_matches_survey_numbers(nh):
     nh.compute_rhs(None, *velocities("wminus1", 64, 64, 64)); nh.solve_p()
     hg, _ = nh.history()
     ref = [1.0, 7.2958980741680756e-04, 3.1837738515430506e-06, 4.2003277907156717e-08, 8.5429640221199814e-10]
-    for a, b in zip(hg, ref):
-        assert abs(a - b) <= 1e-6 * b, (hg, ref)
+    tol = [1e-15, 1e-11, 1e-10, 1e-6, 1e-5]                  # two independent restatements drift apart like ~1.4e-17/res
+    for a, b, t in zip(hg, ref, tol):
+        assert abs(a - b) <= t * b, (hg, ref)
     assert hg[-1] <= 1e-12 and len(hg) == 7
 
 

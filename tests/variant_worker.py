@@ -2,7 +2,7 @@
 library reads once per process: MGB_NO_SMALL_KERNEL, MGB_NO_MID_KERNEL, MGB_NO_FUSED_HALO, MGB_NO_FUSED_RELAX,
 MGB_FUSED_MIN_TILES, MGB_F_GRID_CAP, MGB_F_VARIANT ...) can force a code path that the grid size would not select.
 
-    python tests/variant_worker.py KIND NX NY NZ [solve]
+    python tests/variant_worker.py KIND NX NY NZ [solve] [bench]     (bench: dx = dy = 156.25 m as in bench.py)
 
 Prints "OK ..." and exits 0 when the CUDA path matches the CPU oracle (bit-exact against its rank-1 formulation)."""
 import os
@@ -18,12 +18,13 @@ from common import history_close, make_oracle, make_product, neumann_halo, rando
 
 def main():
     kind, nx, ny, nz = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
-    do_solve = len(sys.argv) > 5 and sys.argv[5] == "solve"
+    do_solve = "solve" in sys.argv[5:]
+    bench_dx = "bench" in sys.argv[5:]
     from mgroms_b200 import nhydro as nh
     nh.load(); nh.reset_params()
     prm = dict(solver_prec=1e-10, solver_maxiter=20)
-    o1 = make_oracle(kind, nx, ny, nz, relax_order=1, **prm)
-    make_product(nh, kind, nx, ny, nz, **prm)
+    o1 = make_oracle(kind, nx, ny, nz, relax_order=1, bench_dx=bench_dx, **prm)
+    make_product(nh, kind, nx, ny, nz, bench_dx=bench_dx, **prm)
     worst = 0.0
     paths = [nh.relax_path(lev) for lev in range(1, o1.nlevs + 1)]
     want = os.environ.get("MGB_EXPECT_PATH")
