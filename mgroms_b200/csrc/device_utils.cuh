@@ -91,6 +91,16 @@ __device__ __forceinline__ double thomas_smem(double* __restrict__ x, const doub
   return xm;
 }
 
+// the plain loops on the same {pivot, off-diagonal} layout (any nz)
+__device__ __forceinline__ double thomas_smem_plain(double* x, const double2* bu, int nz) {
+  double2 c = bu[0];
+  double xm = x[0] * c.x;
+  x[0] = xm;
+  for (int k = 1; k < nz; ++k) { const double udp = c.y; c = bu[k]; xm = (x[k] - udp * xm) * c.x; x[k] = xm; }
+  for (int k = nz - 2; k >= 0; --k) { c = bu[k]; xm = x[k] - (c.y * c.x) * xm; x[k] = xm; }
+  return xm;
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 

@@ -9,7 +9,8 @@ extern long long g_launches;   // number of kernel launches issued by this libra
 void kernels_init();           // one-time function attributes (dynamic shared memory limits), occupancy-derived grid caps
 void note_launch_error(cudaError_t e);   // remembers the first failing launch ...
 cudaError_t take_launch_error();         // ... for the next API boundary (solver.cu: finish)
-int device_sm_count();                   // SMs of the current device (grid caps are derived from it, not hard-coded)
+int device_sm_count();
+int thomas_variant();                    // MGB_THOMAS (experiments): 0 plain loops, 1 prefetching form                   // SMs of the current device (grid caps are derived from it, not hard-coded)
 
 // ---- halo (single-GPU part: physical edges; src/mg_mpi_exchange.f90) ---------------------------------
 // nh = 1 array a(nzl, 0:ny+1, 0:nx+1): homogeneous-Neumann mirror on edges without neighbour, physical corners.

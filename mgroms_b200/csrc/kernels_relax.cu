@@ -192,7 +192,7 @@ __device__ __forceinline__ void cone_recur(const LevelView& L, int rb, double xv
 // barrier ids: 1,2 = slot full (producers -> Thomas) ; 3,4 = solved (Thomas -> recurrence) ; 5,6 = s ready (recurrence -> producers)
 template <int NZ, int NPW, int MINB>
 __global__ void __launch_bounds__((NPW + 2) * 32, MINB)
-k_relax_F(LevelView L, int rb, int mirror, const double* __restrict__ x1old, double* __restrict__ x1new, int ntj, int ntiles, int dbg) {
+k_relax_F(LevelView L, int rb, int mirror, const double* __restrict__ x1old, double* __restrict__ x1new, int ntj, int ntiles, int dbg, int thv) {
   using G = FGeom<NZ>;
   extern __shared__ __align__(16) double sm[];
   __shared__ int s_off[40];
@@ -324,7 +324,7 @@ k_relax_F(LevelView L, int rb, int mirror, const double* __restrict__ x1old, dou
         const int r = c / G::TJ, cj = c - r * G::TJ;
         const int i = c0 + r, m = mA + cj;
         if (i > nx || m >= nyc) continue;
-        const double xm = thomas_smem<NZ>(s_rhs + c * G::PITCH, s_bu + c * G::PITCH);
+        const double xm = thv ? thomas_smem<NZ>(s_rhs + c * G::PITCH, s_bu + c * G::PITCH) : thomas_smem_plain(s_rhs + c * G::PITCH, s_bu + c * G::PITCH, NZ);
         st_tagged(q1t + (size_t)(1 + ((i + rb) & 1) + 2 * m) + (size_t)ny2 * i, xm, ep);
       }
       __threadfence_block();
@@ -411,7 +411,7 @@ void launch_F(cudaStream_t st, const LevelView& L, int rb, int mirror, const dou
   if (cap < 32 || ntiles < 32) { note_launch_error(cudaErrorLaunchOutOfResources); return; }
   const int grid = ntiles < cap ? ntiles : cap;
   static const int dbg = []() { const char* e = std::getenv("MGB_F_SKIP_S"); return (e && e[0] == '1') ? 1 : 0; }();   // timing experiments only: s = 0
-  launch_k(k_relax_F<NZ, NPW, MINB>, grid, (NPW + 2) * 32, fused_smem_bytes<NZ>(), st, L, rb, mirror, x1old, x1new, ntj, ntiles, dbg);
+  launch_k(k_relax_F<NZ, NPW, MINB>, grid, (NPW + 2) * 32, fused_smem_bytes<NZ>(), st, L, rb, mirror, x1old, x1new, ntj, ntiles, dbg, thomas_variant());
 }
 
 template <int NZ>
@@ -433,8 +433,7 @@ void relax_fused_init() {
 #undef MGB_F_CAP
 }
 bool relax_fused_supported(const LevelView& L) {
-  static const bool off = []() { const char* e = std::getenv("MGB_NO_FUSED_RELAX"); return e && e[0] == '1'; }();
-  if (off || !L.q1t || !L.tctl || !L.err || !L.abort_flag) return false;
+  if (!L.q1t || !L.tctl || !L.err || !L.abort_flag) return false;
   if (!(L.nz == 32 || L.nz == 64 || L.nz == 128)) return false;   // levels with fewer layers are small: cooperative / single-CTA kernels
   if (L.rb_chunk != RB_CHUNK || (L.ny & 1)) return false;
   const int TJ = 128 / L.nz, TC = RB_CHUNK * TJ;

@@ -439,7 +439,7 @@ static void relax_tiling(const LevelView& L, const ColourSet& cs, int& TI, int& 
 // and e -> (k, column) is a shift; 0: generic.  tj_shift >= 0 when TJ is a power of two.  All element indices are 32-bit
 // (a level holds < 2^31 points per GPU): one IMAD.WIDE per operand array instead of 64-bit add chains.
 template <int MINB, int NZC>
-__global__ void __launch_bounds__(256, MINB) k_relax_A4(LevelView L, ColourSet cs, int TI, int TJ, int ntj, int ntiles, int tj_shift) {
+__global__ void __launch_bounds__(256, MINB) k_relax_A4(LevelView L, ColourSet cs, int TI, int TJ, int ntj, int ntiles, int tj_shift, int thv) {
   extern __shared__ __align__(16) double sm[];
   const int nz = NZC ? NZC : L.nz, ny2 = L.ny + 2, pitch = nz + 1;
   const int TC = TI * TJ;
@@ -559,14 +559,7 @@ __global__ void __launch_bounds__(256, MINB) k_relax_A4(LevelView L, ColourSet c
         const int j = colour_jstart(cs, i) + 2 * (tile_j * TJ + cj);
         if (j > L.ny || j < 1) continue;
         double* x = s_rhs + c * pitch; const double2* bu = s_bu + c * pitch;
-        double xm;
-        if (NZC) xm = thomas_smem<NZC ? NZC : 2>(x, bu);
-        else {
-          xm = x[0] * bu[0].x;
-          x[0] = xm;
-          for (int k = 1; k < nz; ++k) { xm = (x[k] - bu[k - 1].y * xm) * bu[k].x; x[k] = xm; }
-          for (int k = nz - 2; k >= 0; --k) { xm = x[k] - (bu[k].y * bu[k].x) * xm; x[k] = xm; }
-        }
+        const double xm = (NZC && thv) ? thomas_smem<NZC ? NZC : 2>(x, bu) : thomas_smem_plain(x, bu, nz);
         if (cs.bottom_mode == 1) L.q1[(size_t)j + (size_t)ny2 * i] = xm;
       }
       __syncwarp();
@@ -575,14 +568,18 @@ __global__ void __launch_bounds__(256, MINB) k_relax_A4(LevelView L, ColourSet c
     }
   }
 }
+// 0: plain Thomas loops (shared-memory loads on the dependent chain) ; 1: operands of the next four levels prefetched.
+// Measured inside the kernels (profiles/summary_r02.md): the prefetching form issues its loads in bursts that the in-order
+// warp cannot overlap with its own FP64 chain, and is slower where the Thomas warp is critical (nz = 128) -> default 0.
+int thomas_variant() { static const int v = []() { const char* e = std::getenv("MGB_THOMAS"); return e ? std::atoi(e) : 0; }(); return v; }
 template <int MINB>
 static void launch_A4_nz(cudaStream_t st, const LevelView& L, const ColourSet& cs, int grid, size_t smem, int TI, int TJ, int ntj, int ntiles, int tj_shift) {
   switch (L.nz) {
-    case 128: launch_k(k_relax_A4<MINB, 128>, grid, 256, smem, st, L, cs, TI, TJ, ntj, ntiles, tj_shift); break;
-    case 64: launch_k(k_relax_A4<MINB, 64>, grid, 256, smem, st, L, cs, TI, TJ, ntj, ntiles, tj_shift); break;
-    case 32: launch_k(k_relax_A4<MINB, 32>, grid, 256, smem, st, L, cs, TI, TJ, ntj, ntiles, tj_shift); break;
-    case 16: launch_k(k_relax_A4<MINB, 16>, grid, 256, smem, st, L, cs, TI, TJ, ntj, ntiles, tj_shift); break;
-    default: launch_k(k_relax_A4<MINB, 0>, grid, 256, smem, st, L, cs, TI, TJ, ntj, ntiles, tj_shift); break;
+    case 128: launch_k(k_relax_A4<MINB, 128>, grid, 256, smem, st, L, cs, TI, TJ, ntj, ntiles, tj_shift, thomas_variant()); break;
+    case 64: launch_k(k_relax_A4<MINB, 64>, grid, 256, smem, st, L, cs, TI, TJ, ntj, ntiles, tj_shift, thomas_variant()); break;
+    case 32: launch_k(k_relax_A4<MINB, 32>, grid, 256, smem, st, L, cs, TI, TJ, ntj, ntiles, tj_shift, thomas_variant()); break;
+    case 16: launch_k(k_relax_A4<MINB, 16>, grid, 256, smem, st, L, cs, TI, TJ, ntj, ntiles, tj_shift, thomas_variant()); break;
+    default: launch_k(k_relax_A4<MINB, 0>, grid, 256, smem, st, L, cs, TI, TJ, ntj, ntiles, tj_shift, thomas_variant()); break;
   }
 }
 template <int MINB> static void a4_attrs() {
@@ -1068,7 +1065,7 @@ __global__ void __launch_bounds__(512, 1) k_relax_mid(LevelView L, int nsweeps, 
       }
       __syncthreads();
       for (int cl = threadIdx.x; cl < tcn; cl += blockDim.x) {
-        const double xm = thomas_smem<NZ>(s_rhs + cl * pitch, s_bu + cl * pitch);
+        const double xm = thomas_smem_plain(s_rhs + cl * pitch, s_bu + cl * pitch, NZ);
         if (rank1) { const int c = cbase + cl; const int i = 1 + c / nyc, jc = c - (i - 1) * nyc; L.q1[1 + ((i + rb) & 1) + 2 * jc + ny2 * i] = xm; }
       }
       __syncthreads();

@@ -111,7 +111,7 @@ struct Solver {
   bool use_graph = true;             // replay one captured F-cycle (+ residual) per outer iteration
   bool fuse_halo = true;             // neighbour-free levels: relax kernels write the Neumann halo themselves
   bool fuse_exchange = true;         // small / mid levels with neighbour ranks: the relax kernel runs the peer-memory exchange itself
-  bool use_fused = true;             // big levels: one persistent launch per colour (A + B + C fused)
+  bool use_fused = false;            // big levels: one persistent launch per colour (A + B + C fused)
   bool fuse_bc = true;               // neighbour-free levels: kernels B and C fused
   size_t fuse_bc_limit = 3000000;    // ... up to this many points (larger levels stream better with the separate C)
   cudaGraphExec_t cycle_graph = nullptr;
@@ -819,7 +819,9 @@ static int init(int nx, int ny, int nz, int npx, int npy, int rank, const char* 
   const char* nf = std::getenv("MGB_NO_FUSED_HALO");
   S.fuse_halo = !(nf && nf[0] == '1');
   { const char* nfe = std::getenv("MGB_NO_FUSED_EXCHANGE"); S.fuse_exchange = !(nfe && nfe[0] == '1'); }
-  { const char* nfr = std::getenv("MGB_NO_FUSED_RELAX"); S.use_fused = !(nfr && nfr[0] == '1'); }
+  // the one-launch-per-colour kernel is correct but not yet faster than A + B + C (its Thomas / recurrence warps are the
+  // critical path, profiles/summary_r02.md): opt-in
+  { const char* fr = std::getenv("MGB_FUSED_RELAX"); S.use_fused = fr && fr[0] == '1'; }
   const char* nb = std::getenv("MGB_NO_FUSED_BC");
   S.fuse_bc = !(nb && nb[0] == '1');
   { const char* fl = std::getenv("MGB_FUSE_BC_LIMIT"); if (fl) S.fuse_bc_limit = (size_t)std::atoll(fl); }

@@ -1,5 +1,5 @@
 """Runs one relaxation / solve parity check in a fresh process, so that kernel-selection knobs (environment variables the
-library reads once per process: MGB_NO_SMALL_KERNEL, MGB_NO_MID_KERNEL, MGB_NO_FUSED_HALO, MGB_NO_FUSED_RELAX,
+library reads once per process: MGB_NO_SMALL_KERNEL, MGB_NO_MID_KERNEL, MGB_NO_FUSED_HALO, MGB_FUSED_RELAX,
 MGB_FUSED_MIN_TILES, MGB_F_GRID_CAP, MGB_F_VARIANT ...) can force a code path that the grid size would not select.
 
     python tests/variant_worker.py KIND NX NY NZ [solve] [bench]     (bench: dx = dy = 156.25 m as in bench.py)
