@@ -46,9 +46,9 @@ __device__ __host__ __forceinline__ int cone_hw(int d) { return (d + 1) >> 1; }
 // A tag that never arrives (a lost CTA, a bug) must not hang the GPU: after L.timeout_ms of wall clock the wait gives up and
 // raises the mapped host word (the API call fails at its end) and the device abort flag (later waits return at once).
 __device__ __forceinline__ uint4 ld_tagged_raw(const uint4* src) {
-  uint4 w;
-  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(src) : "memory");
-  return w;
+  unsigned long long a, b;                                     // two single-copy-atomic halves {lo | tag << 32, hi | tag << 32}
+  asm volatile("ld.relaxed.gpu.global.v2.b64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(src) : "memory");
+  return make_uint4((unsigned)a, (unsigned)(a >> 32), (unsigned)b, (unsigned)(b >> 32));
 }
 // w was read from src; re-read until both tags carry the launch number
 __device__ __forceinline__ double tagged_value(uint4 w, const uint4* src, unsigned ep, const LevelView& L) {
@@ -66,9 +66,12 @@ __device__ __forceinline__ double tagged_value(uint4 w, const uint4* src, unsign
   }
   return __longlong_as_double((long long)(((unsigned long long)w.z << 32) | w.x));
 }
+// gpu-scope relaxed stores of the two 64-bit halves {lo | tag << 32, hi | tag << 32}: each half is single-copy atomic, which is all
+// the reader needs (st.volatile would be system scope: the fences behind it then wait for system-level visibility)
 __device__ __forceinline__ void st_tagged(uint4* dst, double v, unsigned ep) {
   const unsigned long long u = (unsigned long long)__double_as_longlong(v);
-  asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "r"((unsigned)u), "r"(ep), "r"((unsigned)(u >> 32)), "r"(ep) : "memory");
+  const unsigned long long a = (u & 0xffffffffull) | ((unsigned long long)ep << 32), b = (u >> 32) | ((unsigned long long)ep << 32);
+  asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1,%2};" ::"l"(dst), "l"(a), "l"(b) : "memory");
 }
 
 // geometry of the cone of one tile
@@ -320,20 +323,32 @@ k_relax_F(LevelView L, int rb, int mirror, const double* __restrict__ x1old, dou
       named_bar_sync(1 + (n & 1), NALL);
       FT(1)
       const int chunk = tile / ntj, c0 = 1 + chunk * G::CH, mA = (tile - chunk * ntj) * G::TJ;
-      for (int c = lane; c < G::TC; c += 32) {
+      double xq[(G::TC + 31) / 32];
+#pragma unroll
+      for (int u = 0; u < (G::TC + 31) / 32; ++u) {
+        const int c = lane + 32 * u;
         const int r = c / G::TJ, cj = c - r * G::TJ;
         const int i = c0 + r, m = mA + cj;
-        if (i > nx || m >= nyc) continue;
-        const double xm = thv ? thomas_smem<NZ>(s_rhs + c * G::PITCH, s_bu + c * G::PITCH) : thomas_smem_plain(s_rhs + c * G::PITCH, s_bu + c * G::PITCH, NZ);
-        st_tagged(q1t + (size_t)(1 + ((i + rb) & 1) + 2 * m) + (size_t)ny2 * i, xm, ep);
+        xq[u] = 0.0;
+        if (c < G::TC && i <= nx && m < nyc)
+          xq[u] = thv ? thomas_smem<NZ>(s_rhs + c * G::PITCH, s_bu + c * G::PITCH) : thomas_smem_plain(s_rhs + c * G::PITCH, s_bu + c * G::PITCH, NZ);
       }
+      FT(3)
       __threadfence_block();
-      named_bar_arrive(3 + (n & 1), 64);                        // solved: the pivots of this tile are dead, their slot stages the cone
+      named_bar_arrive(3 + (n & 1), 64);                        // solved (shared memory only): the write-back may use the tile
+      FT(4)
+#pragma unroll
+      for (int u = 0; u < (G::TC + 31) / 32; ++u) {             // ... and q1 goes out behind the barrier, no fence waits for it
+        const int c = lane + 32 * u;
+        const int r = c / G::TJ, cj = c - r * G::TJ;
+        const int i = c0 + r, m = mA + cj;
+        if (c < G::TC && i <= nx && m < nyc) st_tagged(q1t + (size_t)(1 + ((i + rb) & 1) + 2 * m) + (size_t)ny2 * i, xq[u], ep);
+      }
       FT(2)
     }
 #ifdef MGB_F_TIMING
     if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == Gd / 2 || blockIdx.x == Gd - 1))
-      printf("F thomas cta %d tiles %d: per tile cycles wait_full=%lld thomas=%lld\n", (int)blockIdx.x, n, ft_acc[1] / max(n, 1), ft_acc[2] / max(n, 1));
+      printf("F thomas cta %d tiles %d: per tile cycles wait_full=%lld thomas=%lld fence+arrive=%lld stores=%lld\n", (int)blockIdx.x, n, ft_acc[1] / max(n, 1), ft_acc[3] / max(n, 1), ft_acc[4] / max(n, 1), ft_acc[2] / max(n, 1));
 #endif
   } else {
     // ---- recurrence warp
