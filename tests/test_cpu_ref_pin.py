@@ -1,0 +1,229 @@
+"""The oracle pinned against the REFERENCE'S OWN SOURCE.
+
+tests/golden/ref_golden.* hold output of the reference's Fortran routines, translated statement by statement to C
+(oracle/f90toc.py; no Fortran compiler in the image) and run on one rank by oracle/refdriver.py.  The CPU oracle
+(oracle/mgoracle.cpp, relax_order=0 = the reference's sweep order) must reproduce them BIT FOR BIT: stencil coefficients on
+every level, right-hand side, the whole residual history, the final pressure and the corrected velocities, for the
+reference's own 64^3 seamount case (BASELINE configs[0]) and for every geometry / namelist switch of the other drivers.
+The rank-1 form the CUDA path uses (relax_order=1) must stay within the north-star tolerances of the same vectors.
+When the translated library is present (this container, or prebuilt on the GPU box) a live sweep over more sizes runs too,
+and the translator itself is checked on hand-written Fortran snippets whose results are known in closed form."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from common import history_close
+from refgolden import digest, load, load_ops, seeded_field, sub
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = load()
+
+
+def oracle_case(c, relax_order):
+    from oracle.pyoracle import make_case
+    nx, ny, nz = c["dims"]
+    return make_case(c["kind"], nx, ny, nz, 1, 1, uvw=c["uvw"], bench_dx=bool(c.get("bench_dx")), relax_order=relax_order,
+                     solver_prec=c["tol"], solver_maxiter=c["maxite"], **c["params"])
+
+
+@pytest.mark.parametrize("c", G["cases"], ids=[c["name"] for c in G["cases"]])
+def test_oracle_reproduces_the_reference_bit_for_bit(c):
+    o = oracle_case(c, 0)
+    assert o.nlevs == c["nlevs"]
+    for lev in range(1, o.nlevs + 1):
+        li = o.level_info(lev)
+        assert [li["nx"], li["ny"], li["nz"]] == c["level_dims"][lev - 1]
+        assert digest(o.get("cA", lev)) == c["sha_cA"][lev - 1], ("cA", lev)
+    o.compute_rhs()
+    assert digest(o.get("b")[1:-1, 1:-1]) == c["sha_b_interior"]
+    o.solve_p()
+    res, conv = o.history()
+    assert [float(x) for x in res] == c["hist_res"], (list(res), c["hist_res"])          # exact equality of every norm
+    assert [float(x) for x in conv[1:len(res)]] == c["hist_conv"]
+    assert digest(o.get("p")) == c["sha_p"]
+    o.correct_uvw()
+    u, v, w = o.get_uvw(0)
+    assert (digest(u), digest(v), digest(w)) == (c["sha_u"], c["sha_v"], c["sha_w"])
+    o.close()
+
+
+@pytest.mark.parametrize("c", [c for c in G["cases"] if c["params"].get("relax_method", "RB") == "RB"], ids=lambda c: c["name"])
+def test_rank1_form_of_the_smoother_stays_within_tolerance_of_the_reference(c):
+    """relax_order=1 (parallel column solves + rank-1 correction, the form of the CUDA kernels) against REFERENCE output:
+    per-cycle norms to 1e-10 relative (+ round-off floor), final p to 1e-9 relative -- the north-star tolerances."""
+    o = oracle_case(c, 1)
+    o.compute_rhs(); o.solve_p()
+    history_close(o.history()[0], np.array(c["hist_res"]))
+    d = np.abs(sub(o.get("p")) - np.array(c["p_sub"])).max()
+    assert d <= 1e-9 * c["p_max"], d / c["p_max"]
+    o.close()
+
+
+@pytest.mark.parametrize("oc", G["ops_cases"], ids=[c["name"] for c in G["ops_cases"]])
+def test_oracle_operators_one_by_one(oc):
+    from oracle.pyoracle import make_case
+    from oracle.refdriver import neumann_nh1
+    ops = load_ops(); key = oc["key"]
+    nx, ny, nz = oc["dims"]
+    o = make_case(oc["kind"], nx, ny, nz, 1, 1, uvw="random", relax_order=0, **oc["params"])
+    for lev in range(1, o.nlevs + 1):
+        assert np.array_equal(o.get("cA", lev), ops[f"{key}/cA{lev}"]), lev
+    o.compute_rhs()
+    assert np.array_equal(o.get("b")[1:-1, 1:-1], ops[f"{key}/b"][1:-1, 1:-1])
+    p0 = seeded_field((nx + 2, ny + 2, nz), oc["p0_seed"]); neumann_nh1(p0)
+    o.set("b", ops[f"{key}/b"]); o.set("p", p0)
+    o.relax(1, 1)
+    assert np.array_equal(o.get("p"), ops[f"{key}/p_after_relax1"])
+    assert o.residual(1) == float(ops[f"{key}/res_after_relax1"][0])
+    assert np.array_equal(o.get("r"), ops[f"{key}/r"])
+    o.fine2coarse(1)
+    assert np.array_equal(o.get("b", 2), ops[f"{key}/b2"])
+    p2 = seeded_field(o.get("p", 2).shape, oc["p2_seed"]); neumann_nh1(p2)
+    o.set("p", p2, 2)
+    o.coarse2fine(1)
+    assert np.array_equal(o.get("p"), ops[f"{key}/p_after_prolong"])
+    assert np.array_equal(o.get("r"), ops[f"{key}/r_interp"])
+    o.set("p", p0); o.set("b", ops[f"{key}/b"])
+    o.vcycle(1)
+    assert np.array_equal(o.get("p"), ops[f"{key}/p_after_vcycle"])
+    o.close()
+
+
+def _ref_available():
+    from oracle import refdriver
+    return refdriver.available()
+
+
+@pytest.mark.skipif(not _ref_available(), reason="needs oracle/_ref/libmgref.so (built from /root/reference by oracle/build_ref.py)")
+@pytest.mark.parametrize("kind,nx,ny,nz,prm", [
+    ("seamount", 24, 40, 12, {}), ("rndtopo", 48, 16, 32, {}), ("cuc", 16, 16, 64, {}), ("cuc", 40, 24, 16, dict(bmask=True)),
+    ("rndtopo", 32, 32, 8, dict(relax_method="FC", interp_type="nearest")), ("seamount", 16, 48, 16, dict(relax_method="GS", bmask=True)),
+])
+def test_live_translated_reference_against_oracle(kind, nx, ny, nz, prm):
+    """Sizes / switches beyond the committed vectors, reference and oracle run side by side (non-cubic, non-power-of-two)."""
+    from mgroms_b200 import testcases as tc
+    from oracle.pyoracle import make_case
+    from oracle.refdriver import RefSolver
+    geo = {"seamount": tc.seamount, "rndtopo": tc.rndtopo, "cuc": tc.cuc}[kind](nx, ny, nz, 1, 1, 0)
+    vert = tc.CUC_VERT if kind == "cuc" else tc.SEAMOUNT_VERT
+    R = RefSolver(nx, ny, nz, **prm)
+    rm = tc.bmask_rmask(nx, ny) if prm.get("bmask") else None
+    R.matrices(*geo, rm, vert["hc"], vert["theta_b"], vert["theta_s"])
+    o = make_case(kind, nx, ny, nz, 1, 1, uvw="random", relax_order=0, solver_prec=1e-11, solver_maxiter=12, **prm)
+    assert R.nlevs == o.nlevs
+    for lev in range(1, R.nlevs + 1):
+        for name in ("dx", "dy", "zeta", "h", "zr", "zw", "cw", "cA"):
+            assert np.array_equal(R.get(name, lev), o.get(name, lev)), (name, lev)
+    u, v, w = tc.uvw_random(nx, ny, nz, 1, 1, 0)
+    R.compute_rhs(rm, u, v, w); o.compute_rhs()
+    assert np.array_equal(R.get("b")[1:-1, 1:-1], o.get("b")[1:-1, 1:-1])
+    hr, cr = R.solve_p(1e-11, 12); o.solve_p()
+    ho, co = o.history()
+    assert np.array_equal(hr, ho) and np.array_equal(cr[1:], co[1:len(ho)])
+    assert np.array_equal(R.get("p"), o.get("p")) and np.array_equal(R.get("r"), o.get("r"))
+    R.correct_uvw(u, v, w); o.correct_uvw()
+    for a, b in zip((u, v, w), o.get_uvw(0)):
+        assert np.array_equal(a, b)
+    o.close()
+
+
+SNIPPET = """
+module snip
+  implicit none
+  real(kind=8), parameter :: hlf = 0.5_8
+contains
+  subroutine kernel(n, m, a, b, s, t)
+    integer(kind=4), intent(in) :: n, m
+    real(kind=8), dimension(0:n+1,-1:m+2), intent(inout) :: a
+    real(kind=8), dimension(n), intent(out) :: b
+    real(kind=8), intent(out) :: s
+    integer(kind=4), intent(out) :: t
+    integer(kind=4) :: i, j, k
+    real(kind=8), dimension(:,:), pointer :: w
+    allocate(w(0:n+1,2))
+    w(:,:) = 2._8
+    ! section copies with negative strides and the 2A - B extrapolation
+    a(1:n,m+1:m+2) = a(1:n,m:m-1:-1)
+    a(1:n,-1) = 2._8 * a(1:n,1) - a(1:n,2)
+    a(0,:) = -1.5_8
+    s = 0._8
+    t = 0
+    do i = n, 1, -2            ! negative step
+       t = t + i / 2           ! integer division
+    enddo
+    do j = 1, m
+       do i = 1, n
+          k = 1 + mod(i + j, 2)
+          if (k == 1 .and. .not. (i > 3)) then
+             s = s - a(i,j)**2 * hlf + w(i,1)
+          elseif (k == 2) then
+             s = s + (a(i,j) - a(i-1,j)) / real(i + j, kind=8)
+          else
+             s = s + 1.e-1          ! default-real literal: single precision 0.1
+          endif
+       enddo
+    enddo
+    b(:) = 0._8
+    do i = 1, n
+       b(i) = sum(a(i,1:m)) + max(a(i,1), a(i,m), 0.25_8)
+    enddo
+    select case (trim(mode))
+    case ('x', 'double')
+       s = s * 2._8
+    case default
+       s = -s
+    end select
+    deallocate(w)
+  end subroutine kernel
+end module snip
+"""
+
+
+def test_translator_semantics_on_a_known_snippet(tmp_path):
+    """f90toc on hand-written Fortran (not reference code) whose result is recomputed in NumPy: array sections with negative
+    strides, bounds with negative lower limits, integer division, mod, **2, mixed-precision literals, do with a negative
+    step, if / elseif / else, select case on strings, sum(), max(), allocate / deallocate."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import f90toc
+    src = tmp_path / "snip.f90"; src.write_text(SNIPPET)
+    f90toc.GLOBALS["mode"] = "char"
+    tr = f90toc.Translator({}); tr.add(str(src), ["kernel"])
+    c = tmp_path / "snip.c"
+    c.write_text('const char* g_mode = "double";\n' + tr.emit())
+    so = tmp_path / "snip.so"
+    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-std=gnu11", "-I", os.path.join(ROOT, "oracle", "ref"), str(c), "-lm", "-o", str(so)])
+    L = ctypes.CDLL(str(so))
+    n, m = 7, 5
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal((m + 4, n + 2))            # C-order reversed: a[j + 1, i]
+    a0 = a.copy()
+    b = np.zeros(n); s = ctypes.c_double(); t = ctypes.c_int()
+    PD = ctypes.POINTER(ctypes.c_double)
+    L.ref_kernel(ctypes.c_int(n), ctypes.c_int(m), a.ctypes.data_as(PD), b.ctypes.data_as(PD), ctypes.byref(s), ctypes.byref(t))
+    # the same statements in NumPy (Fortran a(i,j) == e[j + 1, i])
+    e = a0.copy()
+    e[m + 2, 1:n + 1] = e[m + 1, 1:n + 1]; e[m + 3, 1:n + 1] = e[m, 1:n + 1]
+    e[0, 1:n + 1] = 2.0 * e[2, 1:n + 1] - e[3, 1:n + 1]
+    e[:, 0] = -1.5
+    assert np.array_equal(a, e)
+    assert t.value == sum(i // 2 for i in range(n, 0, -2))
+    acc = 0.0
+    for j in range(1, m + 1):
+        for i in range(1, n + 1):
+            k = 1 + (i + j) % 2
+            if k == 1 and not i > 3:
+                acc = acc - e[j + 1, i] * e[j + 1, i] * 0.5 + 2.0
+            elif k == 2:
+                acc = acc + (e[j + 1, i] - e[j + 1, i - 1]) / float(i + j)
+            else:
+                acc = acc + float(np.float32(0.1))
+    assert s.value == acc * 2.0
+    for i in range(1, n + 1):
+        row = 0.0
+        for j in range(1, m + 1):
+            row = row + e[j + 1, i]
+        assert b[i - 1] == row + max(e[2, i], e[m + 1, i], 0.25)
