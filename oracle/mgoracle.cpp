@@ -5,11 +5,14 @@
 // cpu_baseline / --impl reference legs can check and time "what the reference computes".
 // Nothing under mgroms_b200/ may include, link or call this file.
 //
-// PARITY UNPINNED: the reference ships no golden vectors, and no Fortran compiler / MPI exists in
-// this image, so this restatement cannot be checked against reference output.  It is pinned
-// instead by (i) the surveyor's independent NumPy restatement history for seamount 64^3
-// (BASELINE.md section 3), (ii) structural identities of the reference's own formulas
-// (A.1 = 0, interior projection identity compute_rhs(correct_uvw(p)) = b - A p), see tests/.
+// PARITY: PINNED ON ONE RANK AGAINST THE REFERENCE'S OWN SOURCE TEXT.  The reference ships no golden vectors and the
+// image has no Fortran compiler / MPI, so no native reference build exists; instead the reference's Fortran routines are
+// translated statement by statement to C (oracle/f90toc.py, oracle/build_ref.py -> oracle/_ref/libmgref.so) and run by
+// oracle/refdriver.py.  With relax_order = 0 this restatement reproduces that output BIT FOR BIT (coefficients of every
+// level, rhs, the whole residual history, p, u/v/w; tests/test_cpu_ref_pin.py, vectors in tests/golden/ref_golden.*).
+// The MULTI-RANK rules (halo exchange, corner precedence, gather / split, global_sum) are not covered by the translation;
+// they are pinned by properties: halo = global Neumann extension, decomposition invariance, gather/split round trips,
+// the surveyor's NumPy history, A.1 = 0, the projection identity, a SciPy sparse assembly of the sweep (tests/).
 //
 // MPI ranks are emulated: a World holds npx*npy Rank objects in ONE process; every operator is a
 // bulk-synchronous loop over ranks (OpenMP thread per rank), and halo exchange / gather copy
