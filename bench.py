@@ -77,6 +77,26 @@ def global_dims(cfg, n):
     return nx * npx, ny * npy, nz
 
 
+def bind_host_thread_near_gpu(local: int):
+    """N > 1: pin this rank's host thread to the CPUs NVML names as closest to its GPU BEFORE the pinned u, v, w buffers are
+    allocated, so that they live on that NUMA node (with 4-8 ranks the PCIe legs of nhydro_solve otherwise cross sockets).
+    Returns a short description for the JSON line, or None when NVML cannot tell."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(local).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        cpus = sorted(os.sched_getaffinity(0))
+        return f"{len(cpus)} CPUs near the GPU ({cpus[0]}-{cpus[-1]})"
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -335,8 +355,11 @@ def main():
     from mgroms_b200 import nhydro as nh, testcases as tc
 
     torch.cuda.set_device(local)
+    affinity = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if not os.environ.get("MGB_BENCH_NO_AFFINITY"):
+            affinity = bind_host_thread_near_gpu(local)
     npx, npy = PROC_GRID[args.gpus]
     nx, ny, nz = local_dims(cfg, args.gpus)
     kind = cfg["kind"]
@@ -450,6 +473,8 @@ def main():
         }
         if e2e:
             out["e2e"] = e2e
+        if affinity:
+            out["config"]["host_affinity"] = affinity
         if parity:
             out["parity"] = parity
     nh.nhydro_clean()
