@@ -279,13 +279,28 @@ PARITY_CASES = [
 ]
 
 
+def reference_vector(kind, dims, grid, params):
+    """Committed output of the translated reference for a decomposed case (tests/golden/ref_golden.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "ref_golden.json")) as f:
+            cases = json.load(f).get("multi_cases", [])
+    except OSError:
+        return None
+    extras = ",".join(f"{k}={params[k]}" for k in sorted(params) if k not in ("solver_prec", "solver_maxiter"))
+    key = f"{kind} {dims[0]}x{dims[1]}x{dims[2]} per rank on {grid[0]}x{grid[1]}" + (f" [{extras}]" if extras else "")
+    for c in cases:
+        if c["key"] == key:
+            return c
+    return None
+
+
 def parity_check(nh, dist, rank, world, local, npx, npy):
     """Same-decomposition comparison with the CPU oracle: cA bit-exact, b bit-exact, residual history
     (|d| <= 1e-10 res + 2e-15), final p (1e-9).  Both halo transports.  Raises on mismatch."""
     import torch
     from oracle.pyoracle import make_case
     from mgroms_b200 import testcases as tc
-    worst_h, worst_p, transports = 0.0, 0.0, []
+    worst_h, worst_p, transports, n_ref_vectors = 0.0, 0.0, [], 0
     for transport in ("p2p", "nccl"):
         os.environ["MGB_NO_P2P"] = "0" if transport == "p2p" else "1"
         for kind, nx, ny, nz, prm, uvw in PARITY_CASES:
@@ -312,6 +327,17 @@ def parity_check(nh, dist, rank, world, local, npx, npy):
             pg, po = nh.get_field("p"), o.get("p", 1, rank)
             dp = float(np.abs(pg - po).max() / np.abs(po).max())
             used = "p2p" if nh.halo_transport() == "p2p" else "nccl"
+            # the same case as produced by the reference's own Fortran text over an emulated MPI (tests/golden/ref_golden.*)
+            gv = reference_vector(kind, (nx, ny, nz), (npx, npy), prm)
+            if gv is not None:
+                import hashlib
+                dg = lambda a: hashlib.sha256(np.ascontiguousarray(np.asarray(a, dtype=np.float64) + 0.0).tobytes()).hexdigest()
+                ok = ok and all(dg(nh.get_field("cA", l)) == gv["sha_cA"][l - 1][rank] for l in range(1, gv["nlevs"] + 1))
+                ok = ok and dg(nh.get_field("b")[1:-1, 1:-1]) == gv["sha_b_interior"][rank]
+                if gv["hist_res"][-1] < 1.0:
+                    hv = np.array(gv["hist_res"])
+                    hist_ok = hist_ok and len(hv) == len(hg) and bool(np.all(np.abs(hg - hv) <= 1e-10 * hv + 2e-15))
+                n_ref_vectors += 1
             nh.nhydro_clean(); o.close()
             flags = torch.tensor([0.0 if (ok and hist_ok and dp < 1e-9) else 1.0, dh if np.isfinite(dh) else 1e30, dp], dtype=torch.float64, device="cuda")
             dist.all_reduce(flags, op=dist.ReduceOp.MAX)
@@ -324,7 +350,10 @@ def parity_check(nh, dist, rank, world, local, npx, npy):
     os.environ.pop("MGB_NO_P2P", None)
     return {"checked": True, "max_hist_rel": worst_h, "p_rel": worst_p, "cA_b_bitexact": True, "transport": transports,
             "cases": [f"{k} {nx}x{ny}x{nz} per rank, nsmall={p.get('nsmall', 8)}" for k, nx, ny, nz, p, _ in PARITY_CASES],
-            "against": f"CPU oracle with the same {npx}x{npy} decomposition (relax_order=1 form; history tol 1e-10*res+2e-15, p tol 1e-9)"}
+            "against": f"CPU oracle with the same {npx}x{npy} decomposition (relax_order=1 form; history tol 1e-10*res+2e-15, p tol 1e-9)"
+                       + (f"; and {n_ref_vectors} comparisons with the committed vectors of the translated reference run on {npx}x{npy} emulated MPI ranks "
+                          f"(coefficients, rhs bit-exact; history 1e-10)" if n_ref_vectors else ""),
+            "reference_vectors_checked": n_ref_vectors}
 
 
 def main():

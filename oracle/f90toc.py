@@ -71,7 +71,9 @@ def logical_lines(path: str) -> list[str]:
             cur += ln[:-1] + " "
             continue
         cur += ln
-        res.append(_lower_outside_strings(cur).strip())
+        for part in split_top(_lower_outside_strings(cur), ";"):      # `a = 1; b = 2` and stray trailing semicolons
+            if part.strip():
+                res.append(part.strip())
         cur = ""
     return res
 
@@ -318,19 +320,63 @@ class Sym:
         return self.rank > 0 and (self.bounds is None or all(b == (None, None) for b in self.bounds))
 
 
-# members of the reference's grid_type (src/mg_grids.f90:24-65; allocations :170-260): name -> (base, rank)
-GRID_MEMBERS = {n: ("int", 0) for n in ("nx", "ny", "nz", "npx", "npy", "incx", "incy", "gather", "ngx", "ngy", "key", "color", "nd")}
-GRID_MEMBERS.update({n: ("real", 2) for n in ("dx", "dy", "zeta", "h")})
-GRID_MEMBERS.update({n: ("real", 3) for n in ("p", "b", "r", "zr", "zw", "cw", "dzw", "zxdy", "zydx", "dummy3dnz", "dummy3dnzp", "dummy3")})
-GRID_MEMBERS["ca"] = ("real", 4)
-GRID_MEMBERS["neighb"] = ("int", 1)
+def parse_types(lines: list[str]):
+    """Derived-type definitions (`type name ... end type`) and module variables of those types
+    (`type(name), dimension(:), pointer :: var`): ({type: {member: Sym}}, {var: type})."""
+    types, dvars, cur = {}, {}, None
+    for ln in lines:
+        if ln == "contains":
+            break
+        m = re.match(r"type\s+([a-z_]\w*)$", ln)
+        if m:
+            cur = types.setdefault(m.group(1), {}); continue
+        if re.match(r"end\s*type", ln):
+            cur = None; continue
+        if cur is not None:
+            parse_decl(ln, cur); continue
+        m = re.match(r"type\s*\(\s*([a-z_]\w*)\s*\).*::\s*([a-z_]\w*)$", ln)
+        if m:
+            dvars[m.group(2)] = m.group(1)
+    return types, dvars
+
+
+def parse_interfaces(lines: list[str]):
+    """Generic interfaces: {generic name: [specific procedures]}."""
+    out, cur = {}, None
+    for ln in lines:
+        m = re.match(r"interface\s+([a-z_]\w*)$", ln)
+        if m:
+            cur = out.setdefault(m.group(1), []); continue
+        if re.match(r"end\s*interface", ln):
+            cur = None; continue
+        if cur is not None:
+            m = re.match(r"module\s+procedure\s+(.*)$", ln)
+            if m:
+                cur.extend(x.strip() for x in m.group(1).split(","))
+    return out
+
 
 # module-level variables the translated routines read (src/mg_namelist.f90, mg_mpi.f90, mg_grids.f90): name -> base type
 GLOBALS = {"myrank": "int", "nprocs": "int", "bmask": "int", "netcdf_output": "int", "aggressive": "int", "nlevs": "int", "ns_pre": "int",
            "ns_post": "int", "ns_coarsest": "int", "mpi_proc_null": "int", "nsmall": "int", "hlim": "real", "nhtheta_b": "real", "nhtheta_s": "real",
-           "cmatrix": "char", "relax_method": "char", "interp_type": "char", "rp": "kind", "ip": "kind", "lg": "kind"}
+           "cmatrix": "char", "relax_method": "char", "interp_type": "char", "rp": "kind", "ip": "kind", "lg": "kind",
+           "solver_prec": "real", "solver_maxiter": "int",
+           # MPI constants (oracle/ref/ref_prelude.h defines them for the thread-emulated MPI of oracle/ref/ref_mpi.c)
+           "mpi_comm_world": "int", "mpi_request_null": "int", "mpi_double_precision": "int", "mpi_sum": "int", "mpi_status_size": "int"}
 
-DROP_CALLS = {"tic", "toc", "write_netcdf", "cpu_time"}
+# MPI procedures -> run-time functions of oracle/ref/ref_mpi.c; per Fortran argument: buf (address of an array / section),
+# val (integer expression), iref / rref (address of an integer / real variable or element), skip
+MPI_MAP = {
+    "mpi_irecv": ("rmpi_irecv", ["buf", "val", "skip", "val", "val", "val", "iref", "skip"]),
+    "mpi_isend": ("rmpi_isend", ["buf", "val", "skip", "val", "val", "val", "iref", "skip"]),
+    "mpi_waitany": ("rmpi_waitany", ["val", "buf", "iref", "skip", "skip"]),
+    "mpi_allreduce": ("rmpi_allreduce_sum", ["rref", "rref", "val", "skip", "skip", "val", "skip"]),
+    "mpi_allgather": ("rmpi_allgather", ["buf", "val", "skip", "buf", "skip", "skip", "val", "skip"]),
+    "mpi_comm_split": ("rmpi_comm_split", ["val", "val", "val", "iref", "skip"]),
+    "mpi_barrier": ("rmpi_barrier", ["val", "skip"]),
+}
+
+DROP_CALLS = {"tic", "toc", "write_netcdf", "cpu_time", "print_grids", "read_nhnamelist", "mg_mpi_init"}
 INTRINSIC_REAL = {"sqrt": "sqrt", "exp": "exp", "log": "log", "cosh": "cosh", "sinh": "sinh", "tanh": "tanh"}
 
 
@@ -425,7 +471,7 @@ class Unit:
                 t = "int" if s.base == "int" else "double"
                 out.append(f"{t}* {a}" if s.byref else f"{t} {a}")
             elif s.deferred:
-                out.append(f"farr {a}")
+                out.append(f"{'iarr' if s.base == 'int' else 'farr'} {a}")
             else:
                 out.append(f"double* {a}_a" if s.base == "real" else f"int* {a}_a")
         return ", ".join(out) if out else "void"
@@ -437,9 +483,23 @@ class Translator:
         self.unreachable = set(unreachable)   # callees of branches the supported configurations never take (nz == 1, aggressive)
         self.callbacks = callbacks or {}      # fortran name -> (c name, [kinds], {keyword: position})
         self.tmp = 0
+        self.types: dict[str, dict[str, Sym]] = {}     # derived types
+        self.dvars: dict[str, str] = {}                # module variables of derived type: name -> type
+        self.generics: dict[str, list[str]] = {}
+
+    def member(self, node) -> Sym:
+        """Sym of `var(idx)%member`."""
+        base = node[1]
+        if not (base[0] == "call" and base[1][0] == "name" and base[1][1] in self.dvars):
+            raise KeyError(f"member access on {base}")
+        return self.types[self.dvars[base[1][1]]][node[2]]
 
     def add(self, path, names):
         lines = logical_lines(path)
+        t, d = parse_types(lines)
+        self.types.update(t); self.dvars.update(d)
+        for g, specs in parse_interfaces(lines).items():
+            self.generics.setdefault(g, []).extend(specs)
         modsyms = {}
         for d in module_decls(lines):
             parse_decl(d, modsyms)
@@ -472,11 +532,11 @@ class Translator:
                 return GLOBALS[e[1]]
             raise KeyError(f"{u.name}: unknown name {e[1]}")
         if k == "mem":
-            return GRID_MEMBERS[e[2]][0]
+            return self.member(e).base
         if k == "call":
             f = e[1]
             if f[0] == "mem":
-                return GRID_MEMBERS[f[2]][0]
+                return self.member(f).base
             n = f[1]
             if n in u.syms:
                 return u.syms[n].base
@@ -509,8 +569,9 @@ class Translator:
         """C expression of the descriptor of an array-valued node and its rank; None if the node is not an array."""
         if node[0] == "name" and node[1] in u.syms and u.syms[node[1]].rank > 0:
             return node[1], u.syms[node[1]].rank, u.syms[node[1]].base
-        if node[0] == "mem" and GRID_MEMBERS[node[2]][1] > 0:
-            return f"{self.ex(u, node[1])}.{node[2]}", GRID_MEMBERS[node[2]][1], GRID_MEMBERS[node[2]][0]
+        if node[0] == "mem" and self.member(node).rank > 0:
+            m = self.member(node)
+            return f"{self.ex(u, node[1])}.{node[2]}", m.rank, m.base
         return None
 
     def ex(self, u: Unit, e, secmap=None) -> str:
@@ -550,18 +611,18 @@ class Translator:
             raise KeyError(f"{u.name}: unknown name {n}")
         if k == "mem":
             base = self.ex(u, e[1])
-            if GRID_MEMBERS[e[2]][1] > 0 and secmap is not None:
-                return self.element(u, e, [("sec", None, None, None)] * GRID_MEMBERS[e[2]][1], secmap)
+            if self.member(e).rank > 0 and secmap is not None:
+                return self.element(u, e, [("sec", None, None, None)] * self.member(e).rank, secmap)
             return f"{base}.{e[2]}"
         if k == "call":
             f, args = e[1], e[2]
-            if f[0] == "name" and f[1] == "grid" and "grid" not in u.syms:
+            if f[0] == "name" and f[1] in self.dvars and f[1] not in u.syms:
                 assert len(args) == 1
-                return f"GRID_[{self.ex(u, args[0])}]"
+                return f"{f[1].upper()}_[{self.ex(u, args[0])}]"
             d = self.array_desc(u, f)
             if d:
-                if f[0] == "mem" and f[2] == "neighb":
-                    return f"{self.ex(u, f[1])}.neighb[{self.ex(u, args[0])}]"
+                if f[0] == "mem" and not self.member(f).pointer:        # fixed-size member array (neighb(8)): a plain C array
+                    return f"{self.ex(u, f[1])}.{f[2]}[{self.ex(u, args[0])}]"
                 return self.element(u, f, args, secmap)
             n = f[1]
             pos = [a for a in args if a[0] != "kw"]
@@ -603,7 +664,10 @@ class Translator:
             if n == "abs":
                 return ("abs" if self.typeof(u, e) == "int" else "fabs") + f"({self.ex(u, pos[0], secmap)})"
             if n in ("size", "lbound", "ubound"):
-                d = self.array_desc(u, pos[0])
+                node = pos[0]
+                if node[0] == "call" and self.array_desc(u, node[1]) and all(a == ("sec", None, None, None) for a in node[2]):
+                    node = node[1]             # size(a(:,:,:),dim=1)
+                d = self.array_desc(u, node)
                 dim = kw.get("dim") or pos[1]
                 idx = f"({self.ex(u, dim)}) - 1"
                 if n == "size":
@@ -614,7 +678,8 @@ class Translator:
             if n == "trim":
                 return self.ex(u, pos[0])
             if n == "present":
-                return f"({pos[0][1]} != 0)"
+                sy = u.syms[pos[0][1]]
+                return f"({pos[0][1]}_a != 0)" if (sy.rank > 0 and not sy.deferred) else (f"({pos[0][1]}.a != 0)" if sy.rank > 0 else f"({pos[0][1]} != 0)")
             if n == "associated":
                 return f"({self.array_desc(u, pos[0])[0]}.a != 0)"
             raise KeyError(f"{u.name}: unknown function {n}")
@@ -693,12 +758,32 @@ class Translator:
         if e[0] == "name":
             e = ("call", e, [])
         name, args = e[1][1], e[2]
-        if name in DROP_CALLS or name.startswith("mpi_"):
+        if name in DROP_CALLS:
             return [f"{ind}/* call {name}(...) dropped */"]
         if name in self.unreachable:
             return [f"{ind}abort(); /* {name}: branch outside the supported configurations (2-D / aggressive coarsening) */"]
         pos = [a for a in args if a[0] != "kw"]
         kws = {a[1]: a[2] for a in args if a[0] == "kw"}
+        if name in MPI_MAP:
+            cname, spec = MPI_MAP[name]
+            assert len(pos) == len(spec) and not kws, (u.name, name, len(pos))
+            cargs = []
+            for kind, a in zip(spec, pos):
+                if kind == "skip":
+                    continue
+                if kind == "val":
+                    cargs.append(self.ex(u, a))
+                elif kind == "buf":
+                    cargs.append(self.array_pointer(u, a))
+                else:
+                    cargs.append(self.address(u, a))
+            return [f"{ind}{cname}({', '.join(cargs)});"]
+        if name.startswith("mpi_"):
+            raise KeyError(f"{u.name}: MPI procedure {name} has no run-time mapping")
+        if name not in self.units and name in self.generics:
+            name = self.resolve_generic(u, name, pos, kws)
+        if name in self.unreachable:
+            return [f"{ind}abort(); /* {name}: branch outside the supported configurations (2-D / aggressive coarsening) */"]
         if name in self.units:
             cal = self.units[name]
             actual = list(pos) + [None] * (len(cal.args) - len(pos))
@@ -734,6 +819,41 @@ class Translator:
             return [f"{ind}{cname}({', '.join(cargs)});"]
         raise KeyError(f"{u.name}: call to unknown subroutine {name} with {len(pos)} positional arguments")
 
+    def resolve_generic(self, u: Unit, name, pos, kws) -> str:
+        """The specific procedure of a generic interface: by number of arguments and by the rank of array arguments."""
+        for cand in self.generics[name]:
+            if cand in self.unreachable:
+                continue
+            if cand not in self.units:
+                continue
+            cal = self.units[cand]
+            if len(pos) > len(cal.args) or any(k not in cal.args for k in kws):
+                continue
+            given = set(cal.args[:len(pos)]) | set(kws)
+            if any(not cal.syms[f].optional and f not in given for f in cal.args):
+                continue
+            ok = True
+            for f, a in zip(cal.args, pos):
+                d = self.array_desc(u, a)
+                fr = cal.syms[f].rank
+                if d and d[1] != fr:
+                    ok = False
+                if not d and fr > 0 and a[0] != "call":
+                    ok = False
+            if ok:
+                return cand
+        raise KeyError(f"{u.name}: no specific procedure of generic {name} matches {len(pos)} positional arguments")
+
+    def address(self, u: Unit, a) -> str:
+        """Address of a scalar variable or of an array element (actual argument of a by-reference dummy)."""
+        if a[0] == "name" and a[1] in u.syms and u.syms[a[1]].rank == 0:
+            return a[1] if u.syms[a[1]].byref else "&" + a[1]
+        if a[0] == "call" and self.array_desc(u, a[1]) and not any(x[0] == "sec" for x in a[2]):
+            return "&" + self.ex(u, a)
+        if a[0] == "mem" and self.member(a).rank == 0:
+            return "&" + self.ex(u, a)
+        raise SyntaxError(f"{u.name}: cannot take the address of {a}")
+
     def array_pointer(self, u: Unit, a) -> str:
         d = self.array_desc(u, a)
         if d:
@@ -757,9 +877,7 @@ class Translator:
         if fs.rank == 0:
             if not fs.byref:
                 return self.ex(u, a)
-            if a[0] == "name" and a[1] in u.syms and u.syms[a[1]].rank == 0:
-                return a[1] if u.syms[a[1]].byref else "&" + a[1]
-            raise SyntaxError(f"{u.name}: by-reference scalar actual {a}")
+            return self.address(u, a)
         if fs.deferred:
             d = self.array_desc(u, a)
             if not d:
@@ -785,7 +903,7 @@ class Translator:
                 continue
             if s.isarg:
                 if s.rank > 0 and not s.deferred:
-                    out.append(f"  farr {n} = mk{s.rank}({n}_a, {self.bounds_args(u, s.bounds)});")
+                    out.append(f"  {'iarr' if s.base == 'int' else 'farr'} {n} = {'imk' if s.base == 'int' else 'mk'}{s.rank}({n}_a, {self.bounds_args(u, s.bounds)});")
                 continue
             if s.base == "char":
                 out.append(f"  const char* {n} = \"\";")
@@ -796,12 +914,13 @@ class Translator:
                 else:
                     out.append(f"  {t} {n} = 0;")
             elif s.deferred:
-                out.append(f"  farr {n} = {{0}};")
+                out.append(f"  {'iarr' if s.base == 'int' else 'farr'} {n} = {{0}};")
             elif s.base == "real":
                 out.append(f"  farr {n} = fa_alloc{s.rank}({self.bounds_args(u, s.bounds)});")
                 frees.append(n)
             else:
-                out.append(f"  /* integer array {n} not used by the translated statements */")
+                out.append(f"  iarr {n} = ia_alloc{s.rank}({self.bounds_args(u, s.bounds)});")
+                frees.append(n)
         for n, s in u.syms.items():
             if not s.isarg and s.parameter is None and s.rank == 0 and s.base != "char":
                 out.append(f"  (void){n};")
@@ -872,7 +991,7 @@ class Translator:
         # close the double brace of do loops: every `do` opened "{ for (...) {" -- patch the matching closers
         text = self.fix_do_braces(out)
         for n in frees:
-            text.append(f"  fa_free({n});")
+            text.append(f"  {'ia' if u.syms[n].base == 'int' else 'fa'}_free({n});")
         text.append("}")
         return "\n".join(text)
 
@@ -912,15 +1031,19 @@ class Translator:
         if m:
             out = []
             for item in split_top(m.group(2)):
+                e = parse_expr(item)
                 if m.group(1):
-                    out.append(f"{ind}fa_free({item}); {item}.a = 0;")
-                else:
-                    nm = item[:item.index("(")].strip()
-                    bounds = []
-                    for b in split_top(item[item.index("(") + 1:match_paren(item, item.index("("))]):
-                        parts = split_top(b, ":")
-                        bounds.append(("1", parts[0]) if len(parts) == 1 else (parts[0], parts[1]))
-                    out.append(f"{ind}{nm} = fa_alloc{len(bounds)}({self.bounds_args(u, bounds)});")
+                    if e[0] == "name" and e[1] in self.dvars:
+                        out.append(f"{ind}/* deallocate({item}): static storage */"); continue
+                    d = self.array_desc(u, e)
+                    out.append(f"{ind}fa_free({d[0]}); {d[0]}.a = 0;")
+                    continue
+                target, dims = e[1], e[2]
+                if target[0] == "name" and target[1] in self.dvars:
+                    out.append(f"{ind}/* allocate({item}): {target[1].upper()}_ is static storage */"); continue
+                d = self.array_desc(u, target)
+                b = ", ".join((f"{self.ex(u, x[1])}, {self.ex(u, x[2])}" if x[0] == "sec" else f"1, {self.ex(u, x)}") for x in dims)
+                out.append(f"{ind}{d[0]} = {'ia' if d[2] == 'int' else 'fa'}_alloc{len(dims)}({b});")
             return out
         toks = tokenize(ln)
         depth = 0
@@ -943,8 +1066,33 @@ class Translator:
                 return self.assign(u, lhs, rhs, ind)
         raise SyntaxError(f"{u.name}: cannot translate statement {ln!r}")
 
+    def emit_types(self) -> str:
+        """C struct of every derived type + the (thread-local) module arrays of those types; generated, not committed."""
+        out = ["/* generated from the reference's derived types by oracle/f90toc.py */"]
+        for tname, members in self.types.items():
+            out.append("typedef struct {")
+            for n, m in members.items():
+                if m.rank == 0:
+                    out.append(f"  {'int' if m.base == 'int' else 'double'} {n};")
+                elif m.pointer:
+                    out.append(f"  {'iarr' if m.base == 'int' else 'farr'} {n};")
+                else:                     # fixed-size array member, 1-based
+                    out.append(f"  {'int' if m.base == 'int' else 'double'} {n}[{m.bounds[0][1]} + 1];")
+            out.append(f"}} {tname};")
+        for v, t in self.dvars.items():
+            out.append(f"extern __thread {t} {v.upper()}_[REF_MAXLEV];")
+        return "\n".join(out)
+
+    def layout(self) -> dict:
+        """Member lists for the ctypes mirror in oracle/refdriver.py."""
+        lay = {}
+        for tname, members in self.types.items():
+            lay[tname] = [[n, ("int" if m.base == "int" else "double") if m.rank == 0 else (("iarr" if m.base == "int" else "farr") if m.pointer else f"int[{int(m.bounds[0][1]) + 1}]")]
+                          for n, m in members.items()]
+        return {"types": lay, "vars": dict(self.dvars)}
+
     def emit(self) -> str:
-        out = ['#include "ref_prelude.h"', ""]
+        out = ['#include "ref_prelude.h"', '#include "ref_types.h"', ""]
         for u in self.units.values():
             out.append(f"void ref_{u.name}({u.c_params()});")
         out.append("")

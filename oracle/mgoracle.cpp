@@ -5,14 +5,15 @@
 // cpu_baseline / --impl reference legs can check and time "what the reference computes".
 // Nothing under mgroms_b200/ may include, link or call this file.
 //
-// PARITY: PINNED ON ONE RANK AGAINST THE REFERENCE'S OWN SOURCE TEXT.  The reference ships no golden vectors and the
-// image has no Fortran compiler / MPI, so no native reference build exists; instead the reference's Fortran routines are
-// translated statement by statement to C (oracle/f90toc.py, oracle/build_ref.py -> oracle/_ref/libmgref.so) and run by
-// oracle/refdriver.py.  With relax_order = 0 this restatement reproduces that output BIT FOR BIT (coefficients of every
-// level, rhs, the whole residual history, p, u/v/w; tests/test_cpu_ref_pin.py, vectors in tests/golden/ref_golden.*).
-// The MULTI-RANK rules (halo exchange, corner precedence, gather / split, global_sum) are not covered by the translation;
-// they are pinned by properties: halo = global Neumann extension, decomposition invariance, gather/split round trips,
-// the surveyor's NumPy history, A.1 = 0, the projection identity, a SciPy sparse assembly of the sweep (tests/).
+// PARITY: PINNED AGAINST THE REFERENCE'S OWN SOURCE TEXT, ONE RANK AND DECOMPOSED.  The reference ships no golden vectors
+// and the image has no Fortran compiler / MPI, so no native reference build exists; instead the reference's Fortran
+// routines -- the solver AND its MPI layer (fill_halo_*, gather / split, global_sum, define_grids / neighbours / gather
+// families) -- are translated statement by statement to C (oracle/f90toc.py, oracle/build_ref.py -> oracle/_ref/libmgref.so)
+// and run by oracle/refdriver.py with the MPI library calls emulated between threads (oracle/ref/ref_mpi.c).  With
+// relax_order = 0 this restatement reproduces that output BIT FOR BIT on 1, 2x1, 2x2 and 4x2 ranks (level plan, coefficients
+// of every level, rhs, the whole residual history, p, u/v/w; tests/test_cpu_ref_pin.py, vectors in tests/golden/ref_golden.*).
+// Independent properties are tested as well (A.1 = 0, projection identity, SciPy sparse assembly of the sweep, halo = global
+// Neumann extension, decomposition invariance, the surveyor's NumPy history; tests/test_cpu_oracle.py and friends).
 //
 // MPI ranks are emulated: a World holds npx*npy Rank objects in ONE process; every operator is a
 // bulk-synchronous loop over ranks (OpenMP thread per rank), and halo exchange / gather copy

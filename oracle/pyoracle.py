@@ -1,8 +1,8 @@
 """ctypes front-end of the CPU oracle (oracle/mgoracle.cpp).  TEST INFRASTRUCTURE ONLY.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
-this module; the product package mgroms_b200 never does.  Parity: pinned on one rank against the translated reference
-(oracle/refdriver.py, tests/test_cpu_ref_pin.py); multi-rank rules by properties -- see mgoracle.cpp header.
+this module; the product package mgroms_b200 never does.  Parity: pinned against the translated reference, one rank and
+decomposed (oracle/refdriver.py, tests/test_cpu_ref_pin.py) -- see mgoracle.cpp header.
 """
 from __future__ import annotations
 

@@ -1,23 +1,28 @@
-"""refdriver.py -- one-rank driver of the TRANSLATED reference (oracle/_ref/libmgref.so, built by oracle/build_ref.py).
+"""refdriver.py -- driver of the TRANSLATED reference (oracle/_ref/libmgref.so, built by oracle/build_ref.py).
 
 TEST INFRASTRUCTURE (oracle/): used by tests/ and tests/golden/make_ref_golden.py only.
 
-What runs from the reference's own source text (translated statement by statement, see oracle/f90toc.py):
-  find_grid_levels, define_grid_dims (src/mg_grids.f90:468-577), setup_zr_zw (src/mg_zr_zw.f90), define_matrix
-  (src/mg_define_matrix.f90:211-680), compute_rhs, correct_uvw, relax + relax_3D_8_{RB,FC,GS} + relax_3D_8_heart + tridiag,
-  compute_residual(_3D_8), fine2coarse(_3D), coarse2fine(_3D_linear, _3D_nearest), solve_p, Fcycle, Vcycle,
-  fill_halo_2D_bmask.
-What this file restates for ONE rank (no arithmetic beyond copies, the nh = 2 extrapolation 2A - B and the 2x2 averages):
-  * grid allocation with the reference's bounds (src/mg_grids.f90:170-260);
-  * the level loop of define_matrices_topo (src/mg_define_matrix.f90:28-208): copy / 2x2 coarsening of dx, dy, zeta, h;
-  * the physical-boundary branches of fill_halo_2D / _3D / _3D_relax / _4D (src/mg_mpi_exchange.f90:23-352, 396-745,
-    750-1242, 1247-1550): on one rank every neighbour is MPI_PROC_NULL, so only those branches execute.
+Everything on the solver path runs from the reference's own source text (translated statement by statement to C by
+oracle/f90toc.py): nhydro_init -> define_grids / define_neighbours / define_gather_informations (src/mg_grids.f90),
+nhydro_matrices -> define_matrices_topo / setup_zr_zw / define_matrix, compute_rhs, solve_p / Fcycle / Vcycle, relax +
+relax_3D_8_{RB,FC,GS} + relax_3D_8_heart + tridiag, compute_residual, fine2coarse, coarse2fine, correct_uvw, AND the MPI layer:
+fill_halo_2D / _3D / _3D_relax / _4D (src/mg_mpi_exchange.f90), gather / split (src/mg_gather.f90), global_sum.  The MPI calls
+themselves (Isend / Irecv / Waitany / Allreduce / Allgather / Comm_split) are emulated between THREADS by oracle/ref/ref_mpi.c:
+one Python thread = one rank, the translated module variables are thread-local.  Not translated: namelist reading (the
+values are set through setters), NetCDF output, timers.
+
 Arrays are NumPy C-order with reversed dimensions, e.g. Fortran p(nz,0:ny+1,0:nx+1) <-> p[i, j, k-1] of shape (nx+2, ny+2, nz).
+
+    RefSolver(nx, ny, nz, **namelist)                     one rank, runs in the calling thread
+    RefWorld(nx, ny, nz, npx, npy, **namelist)            npx*npy ranks = threads; every call is collective
 """
 from __future__ import annotations
 
 import ctypes as C
+import json
 import os
+import queue
+import threading
 
 import numpy as np
 
@@ -25,22 +30,33 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 class farr(C.Structure):
-    _fields_ = [("a", C.POINTER(C.c_double)), ("lb", C.c_int * 4), ("n", C.c_int * 4)]
+    _fields_ = [("a", C.POINTER(C.c_double)), ("lb", C.c_int * 5), ("n", C.c_int * 5)]
 
 
-_FARR_MEMBERS = ["dx", "dy", "zeta", "h", "p", "b", "r", "zr", "zw", "cw", "dzw", "zxdy", "zydx", "dummy3dnz", "dummy3dnzp", "dummy3", "ca"]
-
-
-class grid_t(C.Structure):
-    _fields_ = [(n, C.c_int) for n in ("nx", "ny", "nz", "npx", "npy", "incx", "incy", "gather", "ngx", "ngy", "key", "color", "nd")] + \
-               [("neighb", C.c_int * 9)] + [(n, farr) for n in _FARR_MEMBERS]
+class iarr(C.Structure):
+    _fields_ = [("a", C.POINTER(C.c_int)), ("lb", C.c_int * 5), ("n", C.c_int * 5)]
 
 
 _lib = None
+_types = {}
 
 
 def available() -> bool:
     return os.path.exists(os.path.join(HERE, "_ref", "libmgref.so")) or os.path.isdir("/root/reference/src")
+
+
+def _ctype_of(kind: str):
+    if kind == "int":
+        return C.c_int
+    if kind == "double":
+        return C.c_double
+    if kind == "farr":
+        return farr
+    if kind == "iarr":
+        return iarr
+    if kind.startswith("int["):
+        return C.c_int * int(kind[4:-1])
+    raise ValueError(kind)
 
 
 def lib():
@@ -52,13 +68,16 @@ def lib():
         so = os.path.join(HERE, "_ref", "libmgref.so")
         if os.path.isdir("/root/reference/src") or not os.path.exists(so):
             so = build_ref.build(quiet=True)
+        with open(os.path.join(HERE, "_ref", "layout.json")) as f:
+            lay = json.load(f)
+        for tname, members in lay["types"].items():          # ctypes mirror of grid_type / mpi_buffers (generated layout)
+            _types[tname] = type(tname, (C.Structure,), {"_fields_": [(n, _ctype_of(k)) for n, k in members]})
         L = C.CDLL(so)
-        L.ref_grid.restype = C.POINTER(grid_t)
-        L.ref_grid.argtypes = [C.c_int]
         D, I, PD = C.c_double, C.c_int, C.POINTER(C.c_double)
-        L.ref_find_grid_levels.argtypes = [I] * 5
-        L.ref_setup_zr_zw_croco.argtypes = [D, D, D, farr, farr, farr, farr, C.c_char_p]
-        L.ref_define_matrix.argtypes = [I, farr, farr, farr, farr, farr]
+        L.ref_grid.restype = C.POINTER(_types["grid_type"]); L.ref_grid.argtypes = [I]
+        L.ref_nhydro_init.argtypes = [I] * 5
+        L.ref_nhydro_matrices.argtypes = [farr] * 5 + [D] * 3
+        L.ref_nhydro_solve.argtypes = [I, I, I, PD, PD, PD, PD]
         L.ref_compute_rhs.argtypes = [farr] * 4
         L.ref_correct_uvw.argtypes = [farr] * 4
         L.ref_relax.argtypes = [I, I]
@@ -67,9 +86,16 @@ def lib():
         L.ref_coarse2fine.argtypes = [I]
         L.ref_solve_p.argtypes = [D, I]
         L.ref_vcycle.argtypes = [I]
-        L.ref_fill_halo_2d_bmask.argtypes = [I, farr]
+        L.ref_fill_halo_3d_relax.argtypes = [I, PD, C.POINTER(I), C.POINTER(I), C.POINTER(I)]
+        L.ref_fill_halo_3d.argtypes = [I, farr, C.c_char_p]
+        L.ref_fill_halo_2d.argtypes = [I, farr]
+        L.ref_gather_3d.argtypes = [I, farr, farr]
+        L.ref_split.argtypes = [I, farr, farr]
+        L.ref_set_int.argtypes = [C.c_char_p, I]; L.ref_get_int.argtypes = [C.c_char_p]
+        L.ref_set_real.argtypes = [C.c_char_p, D]
         L.ref_set_str.argtypes = [C.c_char_p, C.c_char_p]
         L.ref_history.argtypes = [PD, PD, I]
+        L.rmpi_world_init.argtypes = [I]; L.rmpi_attach.argtypes = [I]
         _lib = L
     return _lib
 
@@ -80,197 +106,83 @@ def desc(a: np.ndarray, lb) -> farr:
     d = farr()
     d.a = a.ctypes.data_as(C.POINTER(C.c_double))
     shp = a.shape[::-1]
-    for q in range(4):
+    for q in range(5):
         d.lb[q] = lb[q] if q < len(shp) else 0
         d.n[q] = shp[q] if q < len(shp) else 0
     return d
 
 
-_HALO_RELAX = C.CFUNCTYPE(None, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int)
-_HALO_ANY = C.CFUNCTYPE(None, C.c_int, farr, C.c_char_p)
+def view(d: farr) -> np.ndarray:
+    """NumPy view (no copy) of an array owned by the translated reference."""
+    rank = sum(1 for q in range(5) if d.n[q] > 0)
+    return np.ctypeslib.as_array(d.a, shape=tuple(d.n[q] for q in range(rank))[::-1])
 
 
 def neumann_nh1(A):
-    """Physical-boundary branches of fill_halo_2D / fill_halo_3D_relax / fill_halo_3D with nh = 1 (src/mg_mpi_exchange.f90:
-    110-200, 507-598, 953-1095): A[i, j, ...] with the ring at index 0 and n+1."""
+    """Homogeneous-Neumann ring of a (nx+2, ny+2[, nz]) array: what fill_halo does on one rank (used by tests to prepare
+    inputs; the solver path itself runs the translated fill_halo_*)."""
     nx, ny = A.shape[0] - 2, A.shape[1] - 2
-    A[1:nx + 1, 0] = A[1:nx + 1, 1]            # south   a(0,1:nx)    = a(1,1:nx)
-    A[nx + 1, 1:ny + 1] = A[nx, 1:ny + 1]      # east    a(1:ny,nx+1) = a(1:ny,nx)
-    A[1:nx + 1, ny + 1] = A[1:nx + 1, ny]      # north
-    A[0, 1:ny + 1] = A[1, 1:ny + 1]            # west
-    A[0, 0] = A[1, 1]                          # south-west  a(0,0) = a(1,1)
-    A[nx + 1, 0] = A[nx, 1]                    # south-east  a(0,nx+1) = a(1,nx)
-    A[nx + 1, ny + 1] = A[nx, ny]              # north-east
-    A[0, ny + 1] = A[1, ny]                    # north-west
+    A[1:nx + 1, 0] = A[1:nx + 1, 1]; A[nx + 1, 1:ny + 1] = A[nx, 1:ny + 1]
+    A[1:nx + 1, ny + 1] = A[1:nx + 1, ny]; A[0, 1:ny + 1] = A[1, 1:ny + 1]
+    A[0, 0] = A[1, 1]; A[nx + 1, 0] = A[nx, 1]; A[nx + 1, ny + 1] = A[nx, ny]; A[0, ny + 1] = A[1, ny]
 
 
-def halo3d(A, nx, ny, lbc):
-    """fill_halo_3D on one rank (src/mg_mpi_exchange.f90:947-1095): A[i + nh - 1 ... ] of shape (nx+2nh, ny+2nh, nz)."""
-    nh = (A.shape[1] - ny) // 2
-    o = nh - 1                                  # Fortran index (j, i) -> A[i + o, j + o]
-    lbc = lbc.decode() if lbc else None
+class _Rank:
+    """The reference API on one emulated rank.  Every method must run in the thread that owns the rank."""
 
-    def P(j, i):                                # slices in Fortran index space (inclusive ranges as tuples)
-        def s(r):
-            if isinstance(r, tuple):
-                lo, hi, st = (r + (1,))[:3]
-                return slice(lo + o, (hi + o + (1 if st > 0 else -1)) if (hi + o + (1 if st > 0 else -1)) >= 0 else None, st)
-            return r + o
-        return (s(i), s(j))
-    full_j, full_i = (1 - nh, ny + nh), (1 - nh, nx + nh)
-    # south
-    if lbc == "v":
-        A[P(1, full_i)] = 0.0
-    else:
-        A[P(0, (1, nx))] = A[P(1, (1, nx))]
-        if nh == 2:
-            A[P(-1, (1, nx))] = 2.0 * A[P(1, (1, nx))] - A[P(2, (1, nx))]
-    # east
-    if lbc == "u":
-        A[P(full_j, nx + 1)] = 0.0
-    else:
-        A[P((1, ny), nx + 1)] = A[P((1, ny), nx)]
-        if nh == 2:
-            A[P((1, ny), nx + 2)] = 2.0 * A[P((1, ny), nx)] - A[P((1, ny), nx - 1)]
-    # north
-    if lbc == "v":
-        A[P(ny + 1, full_i)] = 0.0
-    else:
-        A[P(ny + 1, (1, nx))] = A[P(ny, (1, nx))]
-        if nh == 2:
-            A[P(ny + 2, (1, nx))] = 2.0 * A[P(ny, (1, nx))] - A[P(ny - 1, (1, nx))]
-    # west
-    if lbc == "u":
-        A[P(full_j, 1)] = 0.0
-    else:
-        A[P((1, ny), 0)] = A[P((1, ny), 1)]
-        if nh == 2:
-            A[P((1, ny), -1)] = 2.0 * A[P((1, ny), 1)] - A[P((1, ny), 2)]
-    # corners: mirrors of the interior corner block (p(:,1-nh:0,1-nh:0) = p(:,nh:1:-1,nh:1:-1), ...), or zero with lbc_null
-    lo, hi_j, hi_i = (1 - nh, 0), (ny + 1, ny + nh), (nx + 1, nx + nh)
-    mj_lo, mi_lo, mj_hi, mi_hi = (nh, 1, -1), (nh, 1, -1), (ny, ny - nh + 1, -1), (nx, nx - nh + 1, -1)
-    if lbc == "u":
-        A[P(lo, lo)] = 0.0; A[P(lo, hi_i)] = 0.0; A[P(hi_j, hi_i)] = 0.0; A[P(hi_j, lo)] = 0.0
-    elif lbc == "v":
-        A[P(lo, lo)] = A[P(mj_lo, mi_lo)]; A[P(lo, hi_i)] = A[P(mj_lo, mi_hi)]
-        A[P(hi_j, hi_i)] = 0.0; A[P(hi_j, lo)] = 0.0
-    else:
-        A[P(lo, lo)] = A[P(mj_lo, mi_lo)]; A[P(lo, hi_i)] = A[P(mj_lo, mi_hi)]
-        A[P(hi_j, hi_i)] = A[P(mj_hi, mi_hi)]; A[P(hi_j, lo)] = A[P(mj_hi, mi_lo)]
+    def __init__(self, rank):
+        self.rank, self.L, self.keep = rank, lib(), []
 
+    def init(self, nx, ny, nz, npx, npy, prm):
+        L = self.L
+        L.rmpi_attach(self.rank)
+        L.ref_reset_state()
+        ints = dict(bmask=int(bool(prm.get("bmask", False))), ns_pre=prm.get("ns_pre", 3), ns_post=prm.get("ns_post", 2),
+                    ns_coarsest=prm.get("ns_coarsest", 40), nsmall=prm.get("nsmall", 8), netcdf_output=0, aggressive=0,
+                    solver_maxiter=prm.get("solver_maxiter", 50))
+        for k, v in ints.items():
+            assert L.ref_set_int(k.encode(), int(v)) == 0, k
+        assert L.ref_set_real(b"solver_prec", float(prm.get("solver_prec", 1e-12))) == 0
+        for k, dflt in (("cmatrix", "real"), ("relax_method", "RB"), ("interp_type", "linear")):
+            assert L.ref_set_str(k.encode(), str(prm.get(k, dflt)).encode()) == 0
+        self.bmask = bool(prm.get("bmask", False))
+        self.nx, self.ny, self.nz = nx, ny, nz
+        L.ref_nhydro_init(nx, ny, nz, npx, npy)           # define_grids + define_neighbours (+ gather informations)
+        self.nlevs = L.ref_get_int(b"nlevs")
+        self.dims = {lev: (L.ref_grid(lev).contents.nx, L.ref_grid(lev).contents.ny, L.ref_grid(lev).contents.nz) for lev in range(1, self.nlevs + 1)}
+        return self.nlevs
 
-class RefSolver:
-    """nhydro_init / nhydro_matrices / nhydro_solve of the reference on one MPI rank (src/nhydro.f90:18-143)."""
+    def level_info(self, lev):
+        g = self.L.ref_grid(lev).contents
+        return dict(nx=g.nx, ny=g.ny, nz=g.nz, npx=g.npx, npy=g.npy, incx=g.incx, incy=g.incy, gather=g.gather, ngx=g.ngx, ngy=g.ngy,
+                    key=g.key, neighb=[g.neighb[q] for q in range(1, 9)])
 
-    _active = None
-
-    def __init__(self, nx, ny, nz, bmask=False, relax_method="RB", interp_type="linear", cmatrix="real",
-                 ns_pre=3, ns_post=2, ns_coarsest=40, nsmall=8):
-        L = self.L = lib()
-        RefSolver._active = self
-        for k, v in dict(bmask=int(bmask), ns_pre=ns_pre, ns_post=ns_post, ns_coarsest=ns_coarsest, nsmall=nsmall, myrank=0, nprocs=1,
-                         netcdf_output=0, aggressive=0).items():
-            C.c_int.in_dll(L, "g_" + k).value = v
-        for k, v in dict(cmatrix=cmatrix, relax_method=relax_method, interp_type=interp_type).items():
-            L.ref_set_str(k.encode(), v.encode())
-        self.bmask = bool(bmask)
-        self._cb = (_HALO_RELAX(self._halo_relax), _HALO_ANY(self._halo_any))
-        L.ref_set_callbacks(*self._cb)
-        null = C.c_int.in_dll(L, "g_mpi_proc_null").value
-        # nhydro_init -> grids_init: levels and per-level sizes from the translated find_grid_levels / define_grid_dims
-        g1 = L.ref_grid(1).contents
-        g1.nx, g1.ny, g1.nz, g1.npx, g1.npy, g1.incx, g1.incy = nx, ny, nz, 1, 1, 1, 1
-        L.ref_find_grid_levels(1, 1, nx, ny, nz)
-        self.nlevs = C.c_int.in_dll(L, "g_nlevs").value
-        L.ref_define_grid_dims()
-        self.A = {}                      # (lev, name) -> numpy array (kept alive; the descriptors point into them)
-        self.dims = {}
-        for lev in range(1, self.nlevs + 1):
-            g = L.ref_grid(lev).contents
-            lx, ly, lz = g.nx, g.ny, g.nz
-            self.dims[lev] = (lx, ly, lz)
-            for q in range(9):
-                g.neighb[q] = null
-            g.nd = 8
-            spec = {n: ((lx + 2, ly + 2), (0, 0)) for n in ("dx", "dy", "zeta", "h")}
-            spec.update({n: ((lx + 2, ly + 2, lz), (1, 0, 0)) for n in ("p", "b", "r", "zxdy", "zydx", "dummy3dnz")})
-            spec.update({n: ((lx + 2, ly + 2, lz + 1), (1, 0, 0)) for n in ("cw", "dzw", "dummy3dnzp")})
-            spec["zr"] = ((lx + 4, ly + 4, lz), (1, -1, -1))
-            spec["zw"] = ((lx + 4, ly + 4, lz + 1), (1, -1, -1))
-            spec["ca"] = ((lx + 2, ly + 2, lz, 8), (1, 1, 0, 0))
-            for n, (shape, lb) in spec.items():
-                a = np.zeros(shape)
-                self.A[(lev, n)] = a
-                setattr(g, n, desc(a, lb))
-
-    # ---- call-backs ------------------------------------------------------------------------------------------
-    def _halo_relax(self, lev, ptr, nx, ny, nz):
-        A = np.ctypeslib.as_array(ptr, shape=(nx + 2, ny + 2, nz))
-        neumann_nh1(A)
-
-    def _halo_any(self, lev, d, lbc):
-        rank = sum(1 for q in range(4) if d.n[q] > 0)
-        shape = tuple(d.n[q] for q in range(rank))[::-1]
-        A = np.ctypeslib.as_array(d.a, shape=shape)
-        nx, ny, _ = self.dims[lev]
-        if rank == 2:
-            neumann_nh1(A)
-        elif rank == 3:
-            halo3d(A, nx, ny, lbc)
-        elif rank == 4:
-            if not self.bmask:             # fill_halo_4D (src/mg_mpi_exchange.f90:1325-1410): zero ring unless bmask
-                A[:, 0] = 0.0; A[:, -1] = 0.0; A[0, :] = 0.0; A[-1, :] = 0.0
-
-    # ---- the reference API -----------------------------------------------------------------------------------
     def get(self, name, lev=1):
-        return self.A[(lev, "ca" if name == "cA" else name)]
-
-    def desc_of(self, name, lev):
-        return getattr(self.L.ref_grid(lev).contents, name)
+        return view(getattr(self.L.ref_grid(lev).contents, "ca" if name == "cA" else name.lower()))
 
     def matrices(self, dx, dy, zeta, h, rmask, hc, theta_b, theta_s):
-        """define_matrices_topo (src/mg_define_matrix.f90:28-208); inputs of shape (nx+2, ny+2) = Fortran (0:ny+1,0:nx+1)."""
-        L = self.L
-        C.c_double.in_dll(L, "g_hlim").value = hc
-        C.c_double.in_dll(L, "g_nhtheta_b").value = theta_b
-        C.c_double.in_dll(L, "g_nhtheta_s").value = theta_s
-        for lev in range(1, self.nlevs + 1):
-            nx, ny, nz = self.dims[lev]
-            if lev == 1:
-                for n, src in (("dx", dx), ("dy", dy), ("zeta", zeta), ("h", h)):
-                    self.A[(1, n)][...] = src
-                rmaski = np.ascontiguousarray(rmask, dtype=np.float64) if rmask is not None else np.ones((nx + 2, ny + 2))
-            else:
-                nxf, nyf, _ = self.dims[lev - 1]
-                for n, w in (("dx", 0.5), ("dy", 0.5), ("zeta", 0.25), ("h", 0.25)):
-                    f = self.A[(lev - 1, n)]
-                    # c(1:nyc,1:nxc) = w * ( f(1:nyf:2,1:nxf:2) + f(2:nyf+1:2,1:nxf:2) + f(1:nyf:2,2:nxf+1:2) + f(2:nyf+1:2,2:nxf+1:2) )
-                    self.A[(lev, n)][1:nx + 1, 1:ny + 1] = w * (((f[1:nxf:2, 1:nyf:2] + f[1:nxf:2, 2:nyf + 1:2]) + f[2:nxf + 1:2, 1:nyf:2])
-                                                                + f[2:nxf + 1:2, 2:nyf + 1:2])
-                rmaski = np.ones((nx + 2, ny + 2))
-                if self.bmask:
-                    L.ref_fill_halo_2d_bmask(lev, desc(rmaski, (0, 0)))
-            for n in ("dx", "dy", "zeta", "h"):
-                neumann_nh1(self.A[(lev, n)])
-            L.ref_setup_zr_zw_croco(hc, theta_b, theta_s, self.desc_of("zeta", lev), self.desc_of("h", lev), self.desc_of("zr", lev),
-                                    self.desc_of("zw", lev), b"new_s_coord")
-            halo3d(self.A[(lev, "zr")], nx, ny, None)
-            halo3d(self.A[(lev, "zw")], nx, ny, None)
-            self._rmaski = rmaski
-            L.ref_define_matrix(lev, self.desc_of("dx", lev), self.desc_of("dy", lev), self.desc_of("zr", lev), self.desc_of("zw", lev),
-                                desc(rmaski, (0, 0)))
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (dx, dy, zeta, h)]
+        rm = np.ascontiguousarray(rmask, dtype=np.float64) if rmask is not None else np.ones((self.nx + 2, self.ny + 2))
+        self.keep = arrs + [rm]
+        self.L.ref_nhydro_matrices(*[desc(a, (0, 0)) for a in arrs], desc(rm, (0, 0)), hc, theta_b, theta_s)
 
-    def _uvw_desc(self, u, v, w):
+    def _uvw(self, u, v, w):
         return desc(u, (1, 0, 1)), desc(v, (0, 1, 1)), desc(w, (0, 0, 0))
 
     def compute_rhs(self, rmask, u, v, w):
-        nx, ny, _ = self.dims[1]
-        self._rm = np.ascontiguousarray(rmask, dtype=np.float64) if rmask is not None else np.ones((nx + 2, ny + 2))
-        # rmask is consumed as rmask(j,i) with shape (0:ny+1,0:nx+1) (SURVEY 8b: declared (i,j), used (j,i))
-        self.L.ref_compute_rhs(desc(self._rm, (0, 0)), *self._uvw_desc(u, v, w))
+        self._rm = np.ascontiguousarray(rmask, dtype=np.float64) if rmask is not None else np.ones((self.nx + 2, self.ny + 2))
+        self.L.ref_compute_rhs(desc(self._rm, (0, 0)), *self._uvw(u, v, w))
 
     def correct_uvw(self, u, v, w):
-        self.L.ref_correct_uvw(desc(self._rm, (0, 0)), *self._uvw_desc(u, v, w))
+        self.L.ref_correct_uvw(desc(self._rm, (0, 0)), *self._uvw(u, v, w))
+
+    def nhydro_solve(self, rmask, u, v, w):
+        """The reference's public entry point (src/nhydro.f90:53-102): compute_rhs + solve_p(solver_prec, solver_maxiter) + correct_uvw."""
+        rm = np.ascontiguousarray(rmask, dtype=np.float64) if rmask is not None else np.ones((self.nx + 2, self.ny + 2))
+        PD = C.POINTER(C.c_double)
+        self.L.ref_history_reset()
+        self.L.ref_nhydro_solve(self.nx, self.ny, self.nz, rm.ctypes.data_as(PD), u.ctypes.data_as(PD), v.ctypes.data_as(PD), w.ctypes.data_as(PD))
+        return self.history()
 
     def solve_p(self, tol, maxite):
         self.L.ref_history_reset()
@@ -292,3 +204,72 @@ class RefSolver:
         r = C.c_double(0.0)
         self.L.ref_compute_residual(lev, C.byref(r))
         return r.value
+
+    def fill_halo(self, lev, name):
+        """fill_halo(lev, grid(lev)%name): the generic's 2-D / 3-D specific, exactly as the reference's callers reach it."""
+        d = getattr(self.L.ref_grid(lev).contents, name.lower())
+        rank = sum(1 for q in range(5) if d.n[q] > 0)
+        (self.L.ref_fill_halo_2d if rank == 2 else self.L.ref_fill_halo_3d)(lev, d, *(() if rank == 2 else (None,)))
+
+    def fill_halo_relax(self, lev, name):
+        g = self.L.ref_grid(lev).contents
+        d = getattr(g, name.lower())
+        nx, ny, nz = C.c_int(g.nx), C.c_int(g.ny), C.c_int(d.n[0])
+        self.L.ref_fill_halo_3d_relax(lev, d.a, C.byref(nx), C.byref(ny), C.byref(nz))
+
+
+class RefSolver(_Rank):
+    """One rank, in the calling thread (the common case of the tests)."""
+
+    def __init__(self, nx, ny, nz, **prm):
+        super().__init__(0)
+        self.L.rmpi_world_init(1)
+        self.init(nx, ny, nz, 1, 1, prm)
+
+
+class RefWorld:
+    """npx*npy ranks as threads.  call(method, *args) runs the method on every rank concurrently (a collective), with
+    per-rank arguments given as RefWorld.PerRank([...]); returns the list of per-rank results."""
+
+    class PerRank(list):
+        pass
+
+    def __init__(self, nx, ny, nz, npx, npy, **prm):
+        self.n = npx * npy
+        lib().rmpi_world_init(self.n)
+        self.q_in = [queue.Queue() for _ in range(self.n)]
+        self.q_out = [queue.Queue() for _ in range(self.n)]
+        self.threads = [threading.Thread(target=self._worker, args=(r,), daemon=True) for r in range(self.n)]
+        for t in self.threads:
+            t.start()
+        self.nlevs = self.call("init", nx, ny, nz, npx, npy, prm)[0]
+
+    def _worker(self, r):
+        me = _Rank(r)
+        while True:
+            item = self.q_in[r].get()
+            if item is None:
+                return
+            name, args = item
+            try:
+                self.q_out[r].put(("ok", getattr(me, name)(*args)))
+            except BaseException as e:  # pragma: no cover
+                self.q_out[r].put(("err", repr(e)))
+
+    def call(self, name, *args, timeout=600):
+        for r in range(self.n):
+            self.q_in[r].put((name, tuple(a[r] if isinstance(a, RefWorld.PerRank) else a for a in args)))
+        out = []
+        for r in range(self.n):
+            st, val = self.q_out[r].get(timeout=timeout)
+            if st != "ok":
+                raise RuntimeError(f"rank {r}: {val}")
+            out.append(val)
+        return out
+
+    def get(self, name, lev=1):
+        return [a.copy() for a in self.call("get", name, lev)]
+
+    def close(self):
+        for r in range(self.n):
+            self.q_in[r].put(None)

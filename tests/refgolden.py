@@ -18,8 +18,30 @@ def load():
         return json.load(f)
 
 
+_ARR = None
+
+
 def load_ops():
-    return np.load(os.path.join(HERE, "golden", "ref_golden_ops.npz"))
+    """Operator-level arrays and the sub-sampled fields of the solve cases (keys `<case arrays>/<name>`)."""
+    global _ARR
+    if _ARR is None:
+        _ARR = np.load(os.path.join(HERE, "golden", "ref_golden_ops.npz"))
+    return _ARR
+
+
+def multi_key(kind, dims, grid, params) -> str:
+    """Same identity string as tests/golden/make_ref_golden.py::multi_key."""
+    extras = ",".join(f"{k}={params[k]}" for k in sorted(params) if k not in ("solver_prec", "solver_maxiter"))
+    return f"{kind} {dims[0]}x{dims[1]}x{dims[2]} per rank on {grid[0]}x{grid[1]}" + (f" [{extras}]" if extras else "")
+
+
+def multi_case(kind, dims, grid, params):
+    """The committed reference vector of a decomposed case, or None."""
+    k = multi_key(kind, list(dims), list(grid), params)
+    for c in load().get("multi_cases", []):
+        if c["key"] == k:
+            return c
+    return None
 
 
 def seeded_field(shape, seed):
@@ -30,8 +52,8 @@ def seeded_field(shape, seed):
     return ((k >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0) - 0.5).reshape(shape)
 
 
-def sub(a, stride=(5, 5, 3)):
-    return np.ascontiguousarray(a[::stride[0], ::stride[1], ::stride[2]]).ravel()
+def sub(a, stride):
+    return np.ascontiguousarray(a[::stride[0], ::stride[1], ::stride[2]])
 
 
 def case_ids(cases):
