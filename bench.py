@@ -19,9 +19,10 @@ A "step" is one full solve (all F-cycles until res/bnorm <= 1e-10) with the righ
 H2D of u,v,w + compute_rhs + solve + correct_uvw + D2H inside the timed region.
 For N > 1 the run first checks the live NCCL / peer-memory communicator against the CPU oracle with the SAME
 decomposition on two small cases (both halo transports) and aborts on a mismatch (`parity` in the JSON line).
---impl reference times the CPU oracle (restated reference path, one thread per emulated MPI rank, built -march=native on
-this host) on the same global problem when it fits the host's memory and a time budget; otherwise on the largest
-sub-problem that does, flagged `extrapolated`.
+--impl reference times the reference's own Fortran routines, translated statement by statement to C (oracle/_ref, kind
+"reference"; the C++ port of the oracle, kind "port", only if that library is missing), one thread per MPI rank over a
+thread-emulated MPI, on the same global problem when it fits the host's memory and a time budget; otherwise on the
+largest sub-problem that does, flagged `extrapolated`.
 """
 from __future__ import annotations
 
@@ -193,6 +194,56 @@ def run_oracle(kind, gdims, reps: int, cores: int, nsmall: int):
     return dict(ms=float(np.mean(times)), iters=len(hist) - 1, npx=npx, npy=npy, final=float(hist[-1]), setup_s=setup_s, reps=reps)
 
 
+def run_translated_reference(kind, gdims, reps: int, cores: int, nsmall: int):
+    """Times solve_p of the reference's OWN Fortran routines -- solver and MPI layer, translated statement by statement to C
+    (oracle/f90toc.py; no Fortran compiler in the image), -O3 AVX2+FMA build -- on the global grid `gdims`, one thread per MPI
+    rank over the thread-emulated MPI of oracle/ref/ref_mpi.c.  Same interface as run_oracle."""
+    from oracle import refdriver
+    refdriver.use_fast_build(True)
+    from mgroms_b200 import testcases as tc
+    nxg, nyg, nz = gdims
+    npx, npy = cpu_grid(cores)
+    while nxg // npx < 8 or nyg // npy < 8:
+        if npx >= npy and npx > 1: npx //= 2
+        elif npy > 1: npy //= 2
+        else: break
+    nx, ny, N = nxg // npx, nyg // npy, npx * npy
+    PR = refdriver.RefWorld.PerRank
+    t0 = time.perf_counter()
+    W = refdriver.RefWorld(nx, ny, nz, npx, npy, solver_prec=TOL, solver_maxiter=50, nsmall=nsmall)
+    try:
+        geos, vert = [], None
+        for r in range(N):
+            g, vert = tc.bench_geometry(kind, nx, ny, nz, npx, npy, r)
+            geos.append(g)
+        W.call("matrices", *[PR([g[q] for g in geos]) for q in range(4)], PR([None] * N), vert["hc"], vert["theta_b"], vert["theta_s"], timeout=3600)
+        del geos
+        u, v, w = tc.uvw_wminus1(nx, ny, nz)                      # the same (read-only) arrays for every rank: u = v = 0, w = -1
+        W.call("compute_rhs", PR([None] * N), u, v, w, timeout=3600)
+        del u, v, w
+        setup_s = time.perf_counter() - t0
+        times, hist = [], None
+        for _ in range(reps):
+            t1 = time.perf_counter()
+            hist = W.call("solve_p", TOL, 50, timeout=7200)[0][0]
+            times.append((time.perf_counter() - t1) * 1e3)
+    finally:
+        W.close()
+    return dict(ms=float(np.mean(times)), iters=len(hist) - 1, npx=npx, npy=npy, final=float(hist[-1]), setup_s=setup_s, reps=reps)
+
+
+def cpu_arm():
+    """(runner, kind, description): the translated reference when its prebuilt library is present, else the C++ port."""
+    try:
+        from oracle import refdriver
+        if refdriver.available():
+            return run_translated_reference, "reference", ("the reference's own Fortran routines (solver + MPI layer) translated statement by statement to C "
+                                                          "(oracle/f90toc.py; no Fortran compiler or MPI in this image), gcc -O3 AVX2+FMA, MPI calls emulated between threads")
+    except Exception:
+        pass
+    return run_oracle, "port", "CPU oracle (C++ restatement of the Fortran/MPI path, -O3 -march=native; no Fortran compiler or MPI in this image)"
+
+
 def shrink(gdims, factor):
     """Global grid with `factor` (power of two) times fewer points: the same seamount / topography formula on fewer
     horizontal cells (dx kept), i.e. a bounded sample of the workload."""
@@ -212,9 +263,10 @@ def reference_arm(args, rank, cfg):
     g = global_dims(cfg, args.gpus)
     npts = float(g[0]) * g[1] * g[2]
     nsmall = args.nsmall or cfg["nsmall"]
+    runner, arm_kind, arm_text = cpu_arm()
     # calibration on a small sample of the same workload: CPU rate in point-cycles per second
     cal_dims = shrink(g, max(1, int(2 ** np.ceil(np.log2(max(1.0, npts / 8.4e6))))))
-    cal = run_oracle(cfg["kind"], cal_dims, 1, cores, nsmall)
+    cal = runner(cfg["kind"], cal_dims, 1, cores, nsmall)
     cal_pts = float(cal_dims[0]) * cal_dims[1] * cal_dims[2]
     per_pt_ms = cal["ms"] / cal_pts
     avail = mem_available_bytes()
@@ -229,12 +281,12 @@ def reference_arm(args, rank, cfg):
     if run_pts <= cal_pts:
         r, dims, run_pts = cal, cal_dims, cal_pts
     else:
-        r = run_oracle(cfg["kind"], dims, 1, cores, nsmall)       # one timed solve (tens of seconds of CPU work), whatever --steps says
+        r = runner(cfg["kind"], dims, 1, cores, nsmall)           # one timed solve (tens of seconds of CPU work), whatever --steps says
     scale = npts / run_pts
     value = r["ms"] * scale
     extrap = scale > 1.0 + 1e-9
-    sample = (f"CPU oracle (C++ restatement of the Fortran/MPI path, -O3 -march=native; no Fortran compiler or MPI in this image), "
-              f"{r['npx']}x{r['npy']} emulated ranks = threads on {cores} host cores, {cfg['kind']} {dims[0]}x{dims[1]}x{dims[2]} solved to 1e-10 "
+    sample = (f"{arm_text}, "
+              f"{r['npx']}x{r['npy']} MPI ranks = threads on {cores} host cores, {cfg['kind']} {dims[0]}x{dims[1]}x{dims[2]} solved to 1e-10 "
               f"in {r['iters']} F-cycles, 1 timed solve = {r['ms'] / 1e3:.1f} s (setup {r['setup_s']:.0f} s not counted)")
     if extrap:
         sample += (f"; the job's global grid {g[0]}x{g[1]}x{g[2]} does not fit the host's {avail / 1e9:.0f} GB / the {REF_SOLVE_BUDGET_S:.0f} s budget, "
@@ -249,7 +301,7 @@ def reference_arm(args, rank, cfg):
         "n_gpus": args.gpus, "steps": 1, "warmup": 0, "ms_per_step": value, "higher_is_better": False,
         "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": conf,
         "extrapolated": bool(extrap), "fcycles_per_solve": r["iters"],
-        "cpu_baseline": {"value": value, "unit": "ms", "cores": r["npx"] * r["npy"], "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "ms", "cores": r["npx"] * r["npy"], "kind": arm_kind, "sample": sample},
         "e2e": {"value": value, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -514,9 +566,10 @@ def main():
             cores = os.cpu_count() or 1
             factor = max(1, int(2 ** np.ceil(np.log2(max(1.0, npts / 3.4e7)))))
             sd = shrink((nx, ny, nz), factor)
-            r = run_oracle(kind, sd, 1, cores, args.nsmall or cfg["nsmall"])
-            out["cpu_baseline"] = {"value": r["ms"] * factor, "unit": "ms", "cores": r["npx"] * r["npy"], "kind": "port",
-                                   "sample": f"CPU oracle (restated reference path, -O3 -march=native), {r['npx']}x{r['npy']} emulated MPI ranks = threads on "
+            runner, arm_kind, arm_text = cpu_arm()
+            r = runner(kind, sd, 1, cores, args.nsmall or cfg["nsmall"])
+            out["cpu_baseline"] = {"value": r["ms"] * factor, "unit": "ms", "cores": r["npx"] * r["npy"], "kind": arm_kind,
+                                   "sample": f"{arm_text}, {r['npx']}x{r['npy']} MPI ranks = threads on "
                                              f"{cores} host cores; sample = the same {kind} workload on {sd[0]}x{sd[1]}x{sd[2]} ({r['iters']} F-cycles to 1e-10, "
                                              f"{r['ms']:.0f} ms), scaled x{factor} by grid points to {nx}x{ny}x{nz}"
                                              + ("" if factor > 1 else " (the full grid, nothing scaled)")}

@@ -39,6 +39,14 @@ class iarr(C.Structure):
 
 _lib = None
 _types = {}
+_FAST = False
+
+
+def use_fast_build(on: bool = True):
+    """bench.py's CPU arm: the -O3 / AVX2+FMA build of the same translated text (timing only, never used as a checker)."""
+    global _FAST, _lib
+    if on != _FAST:
+        _FAST, _lib = on, None
 
 
 def available() -> bool:
@@ -66,13 +74,17 @@ def lib():
         sys.path.insert(0, HERE)
         import build_ref
         so = os.path.join(HERE, "_ref", "libmgref.so")
-        if os.path.isdir("/root/reference/src") or not os.path.exists(so):
+        stale = os.path.exists(so) and os.path.getmtime(so) < max(os.path.getmtime(os.path.join(HERE, f)) for f in
+                                                                   ("f90toc.py", "build_ref.py", "ref/ref_prelude.h", "ref/ref_harness.c", "ref/ref_mpi.c"))
+        if not os.path.exists(so) or not os.path.exists(so.replace("libmgref.so", "libmgref_fast.so")) or os.environ.get("MGB_REF_REBUILD") \
+                or (stale and os.path.isdir("/root/reference/src")):
             so = build_ref.build(quiet=True)
         with open(os.path.join(HERE, "_ref", "layout.json")) as f:
             lay = json.load(f)
         for tname, members in lay["types"].items():          # ctypes mirror of grid_type / mpi_buffers (generated layout)
-            _types[tname] = type(tname, (C.Structure,), {"_fields_": [(n, _ctype_of(k)) for n, k in members]})
-        L = C.CDLL(so)
+            if tname not in _types:
+                _types[tname] = type(tname, (C.Structure,), {"_fields_": [(n, _ctype_of(k)) for n, k in members]})
+        L = C.CDLL(so.replace("libmgref.so", "libmgref_fast.so") if _FAST else so)
         D, I, PD = C.c_double, C.c_int, C.POINTER(C.c_double)
         L.ref_grid.restype = C.POINTER(_types["grid_type"]); L.ref_grid.argtypes = [I]
         L.ref_nhydro_init.argtypes = [I] * 5
