@@ -376,7 +376,8 @@ MPI_MAP = {
     "mpi_barrier": ("rmpi_barrier", ["val", "skip"]),
 }
 
-DROP_CALLS = {"tic", "toc", "write_netcdf", "cpu_time", "print_grids", "read_nhnamelist", "mg_mpi_init"}
+DROP_CALLS = {"tic", "toc", "write_netcdf", "cpu_time", "print_grids", "read_nhnamelist", "mg_mpi_init",
+              "mpi_comm_rank", "mpi_comm_size"}      # myrank / nprocs are set when the rank thread attaches
 INTRINSIC_REAL = {"sqrt": "sqrt", "exp": "exp", "log": "log", "cosh": "cosh", "sinh": "sinh", "tanh": "tanh"}
 
 

@@ -107,6 +107,7 @@ def lib():
         L.ref_set_real.argtypes = [C.c_char_p, D]
         L.ref_set_str.argtypes = [C.c_char_p, C.c_char_p]
         L.ref_history.argtypes = [PD, PD, I]
+        L.ref_setup_seamount.argtypes = [I] * 5 + [D] * 3 + [farr] * 4
         L.rmpi_world_init.argtypes = [I]; L.rmpi_attach.argtypes = [I]
         _lib = L
     return _lib
@@ -163,6 +164,12 @@ class _Rank:
         self.nlevs = L.ref_get_int(b"nlevs")
         self.dims = {lev: (L.ref_grid(lev).contents.nx, L.ref_grid(lev).contents.ny, L.ref_grid(lev).contents.nz) for lev in range(1, self.nlevs + 1)}
         return self.nlevs
+
+    def setup_seamount(self, npx, npy, Lx=1.0e4, Ly=1.0e4, Htot=4.0e3):
+        """dx, dy, zeta, h of this rank from the reference's own test set-up (src/mg_setup_tests.f90:108-157)."""
+        out = [np.zeros((self.nx + 2, self.ny + 2)) for _ in range(4)]
+        self.L.ref_setup_seamount(self.nx, self.ny, self.nz, npx, npy, Lx, Ly, Htot, *[desc(a, (0, 0)) for a in out])
+        return out
 
     def level_info(self, lev):
         g = self.L.ref_grid(lev).contents

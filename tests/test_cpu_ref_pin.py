@@ -231,6 +231,31 @@ def test_live_translated_reference_multirank_against_oracle(kind, nx, ny, nz, np
         W.close()
 
 
+@pytest.mark.skipif(not _ref_available(), reason="needs oracle/_ref/libmgref.so")
+def test_seamount_inputs_equal_the_reference_drivers_own_setup():
+    """mgroms_b200/testcases.py::seamount against the translated setup_seamount of the reference's driver
+    (src/mg_setup_tests.f90:108-157), one rank and 2x2 ranks: dx, dy, zeta bit for bit; h to 1 ulp (NumPy's vectorised exp and
+    libm's exp differ in the last bit in a few cells -- it is an INPUT: every implementation under test receives the same array)."""
+    from mgroms_b200 import testcases as tc
+    from oracle.refdriver import RefSolver, RefWorld
+
+    def same(got, want, where):
+        for n, a, b in zip(("dx", "dy", "zeta", "h"), got, want):
+            if n == "h":
+                assert np.abs(a - b).max() <= 2.3e-16 * np.abs(b).max(), (where, n)
+            else:
+                assert np.array_equal(a, b), (where, n)
+    R = RefSolver(16, 24, 8)
+    same(R.setup_seamount(1, 1), tc.seamount(16, 24, 8, 1, 1, 0), "1x1")
+    W = RefWorld(16, 8, 8, 2, 2)
+    try:
+        got = W.call("setup_seamount", 2, 2)
+        for r in range(4):
+            same(got[r], tc.seamount(16, 8, 8, 2, 2, r), f"2x2 rank {r}")
+    finally:
+        W.close()
+
+
 SNIPPET = """
 module snip
   implicit none
