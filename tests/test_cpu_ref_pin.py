@@ -354,3 +354,93 @@ def test_translator_semantics_on_a_known_snippet(tmp_path):
         for j in range(1, m + 1):
             row = row + e[j + 1, i]
         assert b[i - 1] == row + max(e[2, i], e[m + 1, i], 0.25)
+
+
+SNIPPET2 = """
+module snip2
+  implicit none
+  type box_type
+     integer(kind=4) :: n
+     integer(kind=4),dimension(3) :: tag
+     real(kind=8),dimension(:,:),pointer :: a => null()
+  end type box_type
+  type(box_type), dimension(:), pointer :: box
+  interface twice
+     module procedure twice_1d, twice_2d
+  end interface twice
+contains
+  subroutine twice_1d(x, n)
+    integer(kind=4), intent(in) :: n
+    real(kind=8), dimension(n), intent(inout) :: x
+    x(:) = 2._8 * x(:)
+  end subroutine twice_1d
+  subroutine twice_2d(x, scale)
+    real(kind=8), dimension(:,:), pointer, intent(inout) :: x
+    real(kind=8), optional, intent(in) :: scale
+    if (present(scale)) then
+       x(:,:) = scale * x(:,:)
+    else
+       x(:,:) = 2._8 * x(:,:)
+    endif
+  end subroutine twice_2d
+  subroutine driver(lev, m, total, count)
+    integer(kind=4), intent(in) :: lev, m
+    real(kind=8), intent(out) :: total
+    integer(kind=4) :: count
+    integer(kind=4), dimension(4) :: hits
+    real(kind=8), dimension(m) :: v
+    integer(kind=4) :: i, j
+    box(lev)%n = m
+    box(lev)%tag(2) = 7
+    allocate(box(lev)%a(0:m+1,-1:1))
+    do j = -1, 1
+       do i = 0, m+1
+          box(lev)%a(i,j) = real(i,kind=8) + 10._8 * real(j,kind=8)
+       enddo
+    enddo
+    call twice(box(lev)%a)                  ! generic -> twice_2d (rank 2), optional argument absent
+    call twice(box(lev)%a, scale=0.5_8)     ! keyword argument
+    v(:) = box(lev)%a(1:m,1)
+    call twice(v, m)                        ! generic -> twice_1d
+    hits(:) = 0
+    i = 0
+    do while (i < 2*m)
+       i = i + 3
+       hits(1 + mod(i,4)) = hits(1 + mod(i,4)) + 1
+    enddo
+    count = hits(1) + 10*hits(2) + 100*hits(3) + 1000*hits(4) + box(lev)%tag(2)
+    total = sum(v(1:m)) + box(lev)%a(0,-1) + size(box(lev)%a,dim=1)
+    deallocate(box(lev)%a)
+  end subroutine driver
+end module snip2
+"""
+
+
+def test_translator_derived_types_generics_and_integer_arrays(tmp_path):
+    """Second self-test of f90toc on hand-written Fortran: derived type with scalar, fixed-size and pointer members,
+    allocate / deallocate on a member, generic interface resolved by rank, optional and keyword arguments, integer work
+    arrays, do while, by-reference scalar results, size()."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import f90toc
+    src = tmp_path / "snip2.f90"; src.write_text(SNIPPET2)
+    tr = f90toc.Translator({}); tr.add(str(src), ["twice_1d", "twice_2d", "driver"])
+    (tmp_path / "ref_types.h").write_text(tr.emit_types() + "\n")
+    c = tmp_path / "snip2.c"
+    c.write_text(tr.emit() + "\n__thread box_type BOX_[REF_MAXLEV];\n")
+    so = tmp_path / "snip2.so"
+    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-std=gnu11", "-I", os.path.join(ROOT, "oracle", "ref"), "-I", str(tmp_path),
+                           str(c), "-lm", "-o", str(so)])
+    L = ctypes.CDLL(str(so))
+    m = 6
+    total = ctypes.c_double(); count = ctypes.c_int()
+    L.ref_driver(ctypes.c_int(3), ctypes.c_int(m), ctypes.byref(total), ctypes.byref(count))
+    a = np.array([[i + 10.0 * j for j in (-1, 0, 1)] for i in range(m + 2)])        # a[i, j+1]
+    a = 0.5 * (2.0 * a)
+    v = 2.0 * a[1:m + 1, 2]
+    hits = [0, 0, 0, 0]
+    i = 0
+    while i < 2 * m:
+        i += 3
+        hits[i % 4] += 1
+    assert count.value == hits[0] + 10 * hits[1] + 100 * hits[2] + 1000 * hits[3] + 7
+    assert total.value == float(np.sum(v)) + a[0, 0] + (m + 2)
