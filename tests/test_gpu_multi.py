@@ -139,3 +139,27 @@ def test_multi_gpu_matches_oracle_with_same_decomposition(cfg, transport):
                 history_close(res[r]["hist"], np.array(g["hist_res"]))
                 d = np.abs(sub(res[r]["p"], g["sub_stride"]) - load_ops()[f"{g['arrays']}/p_sub_r{r}"]).max()
                 assert d <= 1e-9 * g["p_max"], (r, d / g["p_max"])
+
+
+def test_plain_c_multi_process_driver_over_the_abi(tmp_path):
+    """examples/mg_testseamount_mp.c: the reference's seamount driver on 2x1 ranks as forked plain-C processes (one per GPU),
+    communicator id handed over through pipes -- the compiled-host, no-Python, no-MPI route into the multi-GPU solver.  Its
+    printed history must match the decomposed reference vector of the same case."""
+    import re
+    import subprocess
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "examples", "mg_testseamount_mp")
+    if not os.path.exists(exe):
+        import __graft_entry__
+        __graft_entry__.build()
+    out = subprocess.run([exe, "2", "1", "32", "32", "16"], cwd=tmp_path, capture_output=True, text=True, timeout=300,
+                         env=dict(os.environ, MGB_SPIN_TIMEOUT_MS="5000"))
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    hist = np.array([float(x) for x in re.findall(r"res/bnorm = ([0-9.eE+-]+)", out.stdout)])
+    from common import history_close
+    from refgolden import multi_case
+    g = multi_case("seamount", (32, 32, 16), (2, 1), dict(solver_prec=1e-10, solver_maxiter=20))
+    history_close(hist, np.array(g["hist_res"]))
+    assert os.path.exists(tmp_path / "fort.100")
