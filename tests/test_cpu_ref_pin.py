@@ -256,6 +256,34 @@ def test_seamount_inputs_equal_the_reference_drivers_own_setup():
         W.close()
 
 
+@pytest.mark.skipif(not _ref_available(), reason="needs oracle/_ref/libmgref.so")
+@pytest.mark.parametrize("cfg", [(16, 16, 8, 2, 1, 8), (16, 32, 16, 4, 2, 16), (8, 8, 16, 4, 2, 8), (32, 16, 8, 2, 2, 32), (16, 16, 16, 8, 4, 16),
+                                 (16, 16, 16, 1, 2, 16), (8, 16, 32, 4, 4, 64), (64, 32, 16, 2, 4, 8), (16, 16, 64, 2, 2, 8)])
+def test_product_level_planner_against_the_translated_reference(nh, cfg):
+    """PRODUCT host logic (mgroms_b200/csrc/host_plan.cpp through mgb_plan_levels, no device needed) against the reference's
+    own define_grids / define_grid_dims / define_neighbours / define_gather_informations (src/mg_grids.f90:468-738), translated:
+    number of levels, sizes, process grid, increments, gather flags and factors, the 8 neighbours and the gather key of
+    every rank on every level."""
+    from oracle.refdriver import RefWorld
+    nx, ny, nz, npx, npy, nsmall = cfg
+    nh.set_params(nsmall=nsmall)
+    W = RefWorld(nx, ny, nz, npx, npy, nsmall=nsmall)
+    try:
+        keys = ["nx", "ny", "nz", "npx", "npy", "incx", "incy", "gather", "ngx", "ngy"]
+        plans = [nh.plan_levels(nx, ny, nz, npx, npy, r) for r in range(npx * npy)]
+        assert all(len(p) == W.nlevs for p in plans)
+        for lev in range(1, W.nlevs + 1):
+            infos = W.call("level_info", lev)
+            for r in range(npx * npy):
+                d = plans[r][lev - 1]
+                assert {k: d[k] for k in keys} == {k: infos[r][k] for k in keys}, (r, lev)
+                assert [x if x >= 0 else -1 for x in d["neighb"]] == [x if x >= 0 else -1 for x in infos[r]["neighb"]], (r, lev)
+                if d["gather"]:
+                    assert d["key"] == infos[r]["key"], (r, lev)
+    finally:
+        W.close()
+
+
 SNIPPET = """
 module snip
   implicit none
