@@ -547,6 +547,12 @@ def main():
                 "kernel": f"relax colour half-sweep at level 1 ({nh.relax_path(1)}; halo and bottom-plane upkeep included), 68 B/pt (SURVEY 8d) x {npts} points",
                 "algorithmic_bytes_per_launch": rc["algorithmic_bytes_per_launch"], "kernels": kernels,
                 "relax_paths_by_level": [nh.relax_path(l) for l in range(1, nh.nlevs() + 1)]}
+    # the whole solve against the HBM bound of SURVEY 8(d): one F-cycle + convergence residual = 910 B per level-1 point at level 1,
+    # x 1.3 for the coarser levels = 1.2 kB per level-1 point and cycle
+    solve_bytes = 1.2e3 * npts * max(int(iters), 1)
+    roofline["whole_solve"] = {"algorithmic_bytes": solve_bytes, "achieved": solve_bytes / (ms_per_step * 1e-3) / 1e9, "unit": "GB/s",
+                               "frac": solve_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+                               "note": "1.2 kB per level-1 point and F-cycle (SURVEY 8d) x F-cycles of the solve / measured time per solve"}
 
     if rank == 0:
         out = {
