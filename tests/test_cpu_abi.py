@@ -149,3 +149,14 @@ def test_plain_c_driver_builds_and_fails_loudly_without_gpu(tmp_path):
     exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "mg_testseamount")
     out = subprocess.run([exe, "16", "16", "16"], cwd=tmp_path, capture_output=True, text=True, timeout=120)
     assert out.returncode != 0 and "no usable CUDA device" in out.stderr
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/src/nh_namelist"), reason="needs the reference tree (this container)")
+def test_namelist_reader_on_the_references_own_file(nh):
+    """The namelist file the reference ships (src/nh_namelist), read in place by the product's parser."""
+    d = nh.namelist_probe("/root/reference/src/nh_namelist")
+    assert d["file"] == "1"
+    assert float(d["solver_prec"]) == 1e-12 and d["solver_maxiter"] == "50" and d["nsmall"] == "8"
+    assert (d["ns_coarsest"], d["ns_pre"], d["ns_post"]) == ("40", "3", "2")
+    assert (d["cmatrix"], d["relax_method"], d["interp_type"], d["restrict_type"]) == ("real", "RB", "linear", "avg")
+    assert (d["aggressive"], d["netcdf_output"], d["bmask"]) == ("0", "1", "0")
